@@ -1,0 +1,113 @@
+"""Shared test helpers: golden-fixture loading, seeded parameter generation, error norms."""
+from __future__ import annotations
+
+import glob
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+from oracle import socm_oracle as orc  # noqa: E402  (tests are allowed to use the oracle)
+
+UNET_LAYERS = ["down_0", "down_1", "down_2", "res_0", "res_1", "res_2", "up_2", "up_1", "up_0"]
+
+
+def golden_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def rel_l2(a, b) -> float:
+    """||a-b||_2 / ||b||_2 (norm-wise); 0 if both are exactly zero."""
+    a = torch.as_tensor(a, dtype=torch.float64).reshape(-1)
+    b = torch.as_tensor(b, dtype=torch.float64).reshape(-1)
+    den = float(torch.linalg.norm(b))
+    num = float(torch.linalg.norm(a - b))
+    if den == 0.0:
+        return 0.0 if num == 0.0 else float("inf")
+    return num / den
+
+
+def unet_shapes(d, hdims):
+    h0, h1, h2 = hdims
+    return {
+        "down_0": (h0, d + 1), "down_1": (h1, h0), "down_2": (h2, h1),
+        "res_0": (d, d + 1), "res_1": (h0, h0), "res_2": (h1, h1),
+        "up_2": (h1, h2), "up_1": (h0, h1), "up_0": (d, h0),
+    }
+
+
+def mnet_shapes(d, hdims_M, n_in=2):
+    return {"0": (hdims_M[0], n_in), "2": (hdims_M[1], hdims_M[0]), "4": (d * d, hdims_M[1])}
+
+
+def _seeded(named_shapes, seed, scale):
+    """numpy-seeded uniform(-1,1)/sqrt(fan_in)*scale, weights then bias per layer, in the
+    reference's ``named_parameters`` order (must match oracle/make_golden.py:seeded_params)."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, shape in named_shapes:
+        fan_in = shape[1]
+        w = rng.uniform(-1.0, 1.0, size=shape).astype(np.float32)
+        out[name + ".weight"] = torch.from_numpy(w) * (scale / np.sqrt(fan_in))
+        b = rng.uniform(-1.0, 1.0, size=(shape[0],)).astype(np.float32)
+        out[name + ".bias"] = torch.from_numpy(b) * (scale / np.sqrt(fan_in))
+    return out
+
+
+def seeded_unet(d, hdims, seed, scale=1.0):
+    shp = unet_shapes(d, hdims)
+    return _seeded([(f"{n}.0", shp[n]) for n in UNET_LAYERS], seed, scale)
+
+
+def seeded_mnet(d, hdims_M, seed, scale=0.1, n_in=2):
+    shp = mnet_shapes(d, hdims_M, n_in)
+    return _seeded([(f"sigmoid_layers.{k}", shp[k]) for k in ("0", "2", "4")], seed, scale)
+
+
+class Golden:
+    """One tests/golden/<name>.npz written by oracle/make_golden.py."""
+
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        self.z = z
+        self.name = name
+        self.meta = json.loads(bytes(z["meta_json"]).decode())
+        m = self.meta
+        t = lambda k: torch.from_numpy(z[k].copy())  # noqa: E731
+        kw = {}
+        for k in ("A", "P", "Q", "omega", "kappa", "nu"):
+            if f"setting/{k}" in z.files:
+                kw[k] = t(f"setting/{k}")
+        self.setting = orc.Setting(kind=m["kind"], d=m["d"], sigma=t("setting/sigma"), lmbd=m["lmbd"], **kw)
+        self.x0 = t("setting/x0")
+        self.ts = t("ts")
+        if m.get("param_seed") is not None:
+            self.unet = seeded_unet(m["d"], m["hdims"], m["param_seed"], m["sf_v"])
+            self.mnet = seeded_mnet(m["d"], m["hdims_M"], m["param_seed"] + 1, m["sf_m"],
+                                    3 if m["stopping"] else 2)
+        else:
+            self.unet = {k[5:]: t(k) for k in z.files if k.startswith("unet/")}
+            self.mnet = {k[5:]: t(k) for k in z.files if k.startswith("mnet/")}
+        g = z["gammas"]
+        self.gammas = {"gamma": torch.tensor([float(g[0])]), "gamma2": torch.tensor([float(g[1])]),
+                       "gamma3": torch.tensor([float(g[2])])}
+        self.warm = None
+        if m["warm"]:
+            self.warm = orc.WarmStartTable(t("warm/A_roll"), t("warm/c_roll"), t("warm/A_loss"), t("warm/c_loss"))
+        self.rollout_names = ["states", "noises", "stop_indicators", "fractional_timesteps",
+                              "logw_det", "logw_sto", "logw_term", "controls"]
+        self.traj = tuple(t(f"rollout/{n}") for n in self.rollout_names)
+
+    def grads(self, algo):
+        pre = f"{algo}/grad/"
+        return {k[len(pre):]: torch.from_numpy(self.z[k].copy()) for k in self.z.files if k.startswith(pre)}
+
+    def scalar(self, key):
+        return float(self.z[key])

@@ -1,0 +1,41 @@
+"""Pin the CPU oracle against outputs of the unmodified reference (tests/golden/*.npz,
+written by oracle/make_golden.py).  The reference ships no tests of its own."""
+import pytest
+import torch
+
+from helpers import Golden, golden_names, orc, rel_l2
+
+torch.set_num_threads(1)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_rollout_matches_reference(name):
+    g = Golden(name)
+    B = g.meta["B"]
+    out = orc.rollout(g.setting, g.unet, g.x0.repeat(B, 1), g.ts, noises=g.traj[1], warm=g.warm)
+    for key, mine, ref in zip(g.rollout_names, out, g.traj):
+        if key == "stop_indicators":
+            assert torch.equal(mine.float(), ref), key          # stopping indices: bit-exact
+        else:
+            assert rel_l2(mine, ref) <= 2e-6, (key, rel_l2(mine, ref))
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_loss_and_grads_match_reference(name):
+    g = Golden(name)
+    for algo in g.meta["algorithms"]:
+        unet = {k: v.clone().requires_grad_(True) for k, v in g.unet.items()}
+        mnet = {k: v.clone().requires_grad_(True) for k, v in g.mnet.items()}
+        gam = {k: v.clone().requires_grad_(True) for k, v in g.gammas.items()}
+        obj, wm, ws = orc.socm_loss(g.setting, unet, mnet, gam, g.ts, g.traj, algorithm=algo,
+                                    warm=g.warm, use_stopping_time=g.meta["stopping"])
+        assert abs(float(obj) - g.scalar(f"{algo}/loss")) <= 2e-6 * abs(g.scalar(f"{algo}/loss"))
+        assert abs(float(wm) - g.scalar(f"{algo}/weight_mean")) <= 1e-6 * abs(g.scalar(f"{algo}/weight_mean"))
+        assert abs(float(ws) - g.scalar(f"{algo}/weight_std")) <= 1e-5 * abs(g.scalar(f"{algo}/weight_std")) + 1e-12
+        obj.backward()
+        ref = g.grads(algo)
+        for key, want in ref.items():
+            grp, pname = key.split("/", 1)
+            got = {"unet": unet, "mnet": mnet, "gam": gam}[grp][pname].grad
+            got = torch.zeros_like(want) if got is None else got
+            assert rel_l2(got, want) <= 2e-5, (algo, key, rel_l2(got, want))
