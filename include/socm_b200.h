@@ -1,0 +1,158 @@
+/*
+ * socm_b200.h -- C ABI of the B200-native SOC-matching hot path (libsocm_b200.so).
+ *
+ * This is the drop-in boundary.  The reference (facebookresearch/SOC-matching) is pure
+ * Python/PyTorch and has no FFI of its own; the entry points below are what a binding for
+ * its hot path has to call, one per reference call site (file:line relative to the
+ * reference tree).  INTEGRATION.md shows the ctypes stub a maintainer of the reference
+ * would add in SOC_matching/utils.py and SOC_matching/method.py.
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers (fp32 unless noted), sizes, a cudaStream_t passed as
+ *     void*; no torch types.  Every launcher is asynchronous on `stream`, never allocates,
+ *     never synchronises; workspaces are passed in by the caller.
+ *   - return value 0 = ok, otherwise a socm_status code; socm_last_error() gives the text.
+ *   - all matrices row-major.  "paths" = trajectories (B), "steps" = K = num_steps,
+ *     d = state dimension, grid times ts[0..K].
+ *   - network weights are in torch.nn.Linear layout: W[out][in], b[out].
+ */
+#ifndef SOCM_B200_H_
+#define SOCM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOCM_MAX_DIM 32 /* largest supported state dimension d */
+
+typedef enum {
+  SOCM_OK = 0,
+  SOCM_ERR_INVALID = 1,     /* bad argument (null pointer, d > SOCM_MAX_DIM, ...) */
+  SOCM_ERR_UNSUPPORTED = 2, /* setting / shape the kernels do not cover */
+  SOCM_ERR_CUDA = 3         /* a CUDA runtime call failed */
+} socm_status;
+
+/* experiment_settings/{OU_quadratic,OU_linear,double_well,molecular_dynamics}.py */
+typedef enum {
+  SOCM_OU_QUADRATIC = 0,      /* b=Ax, f=x'Px, g=x'Qx            OU_quadratic.py:51-83 */
+  SOCM_OU_LINEAR = 1,         /* b=Ax, f=0,    g=omega.x         OU_linear.py:43-96    */
+  SOCM_DOUBLE_WELL = 2,       /* b=-4k x(x^2-1), f=0, g=sum nu(x^2-1)^2   double_well.py:43-97 */
+  SOCM_MOLECULAR_DYNAMICS = 3 /* double-well drift, f=1, g=0, Phi=-x_0    molecular_dynamics.py:49-95 */
+} socm_kind;
+
+/* Closed-form problem data (what the reference keeps as attributes of its NeuralSDE
+ * subclass, method.py:15-56).  Unused pointers may be NULL. */
+typedef struct {
+  int32_t kind;              /* socm_kind */
+  int32_t d;
+  int32_t sigma_is_identity; /* 1: skip the d x d products with sigma (results identical) */
+  float lmbd;
+  const float* sigma;       /* [d][d] */
+  const float* sigma_inv;   /* [d][d]  torch.inverse(sigma) */
+  const float* A;           /* [d][d]  OU settings */
+  const float* P;           /* [d][d]  OU_quadratic */
+  const float* Q;           /* [d][d]  OU_quadratic */
+  const float* omega;       /* [d]     OU_linear */
+  const float* kappa;       /* [d]     double_well, molecular_dynamics */
+  const float* nu;          /* [d]     double_well */
+} socm_setting;
+
+/* FullyConnectedUNet (models.py:202-242).  Layer order of the arrays:
+ *   0 down_0 (d+1->h0)  1 down_1 (h0->h1)  2 down_2 (h1->h2)
+ *   3 res_0  (d+1->d)   4 res_1  (h0->h0)  5 res_2  (h1->h1)
+ *   6 up_2   (h2->h1)   7 up_1   (h1->h0)  8 up_0   (h0->d)          (= named_parameters order) */
+typedef struct {
+  int32_t d, h0, h1, h2;
+  const float* w[9];
+  const float* b[9];
+} socm_unet;
+
+/* Warm-start control as a per-grid-time affine table (models.py:163-199 evaluated on the
+ * frozen Gaussian-path spline, gsbm_lib.py:227-306):
+ *     u_ws(t_k, x) = sigma^{-1} ( c_k + A_k x - b(x) ). */
+typedef struct {
+  const float* A; /* [rows][d][d] */
+  const float* c; /* [rows][d]    */
+} socm_warm_table;
+
+/* --- bookkeeping ----------------------------------------------------------------------- */
+int socm_abi_version(void);
+const char* socm_last_error(void);
+/* SM count / opt-in shared memory of the current device (used to size persistent grids). */
+int socm_device_info(int* sm_count, int* smem_optin_bytes);
+
+/* --- K1: Euler-Maruyama rollout  (replaces utils.stochastic_trajectories, utils.py:17-128,
+ *     including NeuralSDE.control, method.py:58-80) ------------------------------------- */
+#define SOCM_ROLLOUT_FORCE_GENERIC 1u /* use the shape-generic kernel even for the default net */
+#define SOCM_ROLLOUT_NO_TRAJ 2u       /* weights-only mode: states/noises/controls may be NULL */
+
+/* step_tab: [5][K] = dt_k, sqrt(lmbd*dt_k), dt_k/lmbd, sqrt(dt_k/lmbd), t_k  computed by the
+ *           caller in fp32 exactly like utils.py:38,47,95-98 (dt from the fp32 linspace).
+ * noise_in: [K][B][d] injected N(0,1) draws, or NULL -> in-kernel Philox4x32-10 keyed by
+ *           (seed, path_offset + path index, step) so results do not depend on the sharding.
+ * outputs:  states [K+1][B][d], noises [K][B][d], controls [K][B][d], stop [K+1][B] (0/1 as
+ *           fp32, utils.py:28,75), eff_dt [K][B] (utils.py:70-78), logw_det/sto/term [B].
+ * warm:     rows = K (rank-2 branch time shift, models.py:170) or NULL.
+ * workspace: socm_rollout_workspace_bytes() bytes (packed weight tape). */
+int64_t socm_rollout_workspace_bytes(const socm_unet* net);
+int socm_rollout_f32(const socm_setting* st, const socm_unet* net, const socm_warm_table* warm,
+                     const float* x0, const float* step_tab, const float* noise_in,
+                     uint64_t seed, uint64_t path_offset, int32_t B, int32_t K,
+                     float* states, float* noises, float* controls, float* stop, float* eff_dt,
+                     float* logw_det, float* logw_sto, float* logw_term,
+                     void* workspace, uint32_t flags, void* stream);
+
+/* Philox4x32-10 + Box-Muller exactly as the rollout draws it: out[k][m][j]. */
+int socm_philox_normal_f32(uint64_t seed, uint64_t path_offset, int32_t B, int32_t K, int32_t d,
+                           float* out, void* stream);
+
+/* UNet at n points: out[n][d] = nabla_V(tx[n][d+1])  (models.py:233-242). */
+int socm_unet_forward_f32(const socm_unet* net, const float* tx, int32_t n, float* out, void* stream);
+
+/* --- SOCM target  (replaces method.py:584-690 after the re-association of SURVEY.md A.3) - */
+/* Right-hand side R[B][ldr] of the block-triangular contraction, per path m:
+ *   cols (2j)d..(2j+1)d   a_jm = eff_dt*grad_f(x_j) - grad_b(x_j) c_jm
+ *   cols (2j+1)d..(2j+2)d c_jm = sqrt(lmbd) sqrt(eff_dt) sigma^{-T} eps_jm + eff_dt sigma^{-T} u_jm
+ *   cols 2Kd..(2K+1)d     grad_g(x_K),            j = 0..K-1,  ldr >= (2K+1)d
+ * and the importance weight w[m] = exp(logw_det+logw_sto+logw_term) (method.py:258-262). */
+int socm_target_prep_f32(const socm_setting* st, const float* states, const float* noises,
+                         const float* controls, const float* eff_dt, const float* logw_det,
+                         const float* logw_sto, const float* logw_term, int32_t B, int32_t K,
+                         float* R, int32_t ldr, float* w, void* stream);
+
+/* target[B][ldt] = R[B][ldr] * L^T,  L[(K+1)d][ldr] = rows (i,k): [M_i0 dM_i0 M_i1 dM_i1 ... M_iK]
+ * (zero for j < i: only K-blocks with j >= i are read). */
+int socm_target_gemm_f32(const float* L, const float* R, int32_t B, int32_t K, int32_t d,
+                         int32_t ldr, float* target, int32_t ldt, void* stream);
+/* dL[(K+1)d][ldr] (+)= G^T R  (contraction over paths), only the j >= i blocks are written. */
+int socm_target_gemm_bwd_f32(const float* G, const float* R, int32_t B, int32_t K, int32_t d,
+                             int32_t ldr, int32_t ldt, float* dL, int32_t accumulate, void* stream);
+/* SOCM_const_M (method.py:289-369): target_i = sum_{j>=i} a_j + grad_g, i.e. M = I, dM = 0. */
+int socm_target_const_m_f32(const float* R, int32_t B, int32_t K, int32_t d, int32_t ldr,
+                            float* target, int32_t ldt, void* stream);
+
+/* --- K3: UNet forward at all (K+1)B points + weighted loss + backward
+ *     (replaces method.py:272-287, 692-720 and loss.backward(), main.py:323) -------------
+ * loss_sums[0] (fp64) += sum_{i,m} s_im w_m |sigma^T (nabla_V(t_i,x_im) [- sigma^{-T} u_ws] - target_im)|^2 * scale
+ * G[B][ldt]     = d loss / d target  (same scale);  grad[...] += d loss / d UNet parameters,
+ * flat in the layer order of socm_unet (w then b per layer).
+ * stop may be NULL (all ones).  warm: rows = K+1 (rank-3 branch, models.py:184-186) or NULL.
+ * workspace: socm_loss_workspace_bytes() bytes. */
+int64_t socm_loss_workspace_bytes(const socm_unet* net, int32_t B, int32_t K);
+int64_t socm_unet_param_count(const socm_unet* net);
+int socm_unet_loss_fwdbwd_f32(const socm_setting* st, const socm_unet* net, const socm_warm_table* warm,
+                              const float* ts, const float* states, const float* target, int32_t ldt,
+                              const float* w, const float* stop, float scale, int32_t B, int32_t K,
+                              float* G, float* grad, double* loss_sums, void* workspace,
+                              uint32_t flags, void* stream);
+
+/* sums[0] += sum w, sums[1] += sum w^2, sums[2] += sum stop  (method.py:715, 903-904);
+ * accumulated in fp64 (warp-shuffle block reduction, one atomic per block). */
+int socm_weight_stats_f32(const float* w, const float* stop, int32_t B, int32_t K, double* sums, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOCM_B200_H_ */

@@ -1,0 +1,151 @@
+// loss.cu -- K3: UNet forward at all (K+1)B trajectory points, importance-weighted squared
+// error against the SOCM target, and the backward pass, in one kernel.
+// Replaces method.py:272-287 (nabla_V at all points, warm-start correction), 692-720 (loss)
+// and the autograd backward of main.py:323 for the UNet parameters and for the target.
+//
+//   loss_generic_kernel  one warp per point, any hdims; parameter gradients by global atomics
+//   (the tiled kernel for the default hdims lives in loss_tile.cu)
+#include "kernels.h"
+#include "unet_generic.cuh"
+
+namespace socm {
+
+struct LossArgs {
+  socm_setting st;
+  const float* warmA;  // [K+1][d][d] or NULL
+  const float* warmc;  // [K+1][d]
+  const float* ts;     // [K+1]
+  const float* states; // [K+1][B][d]
+  const float* target; // [B][ldt]
+  const float* w;      // [B]
+  const float* stop;   // [K+1][B] or NULL
+  float scale;
+  int B, K, ldt;
+  float* G;            // [B][ldt]
+  double* loss_sums;
+};
+
+// Per-point loss and d loss / d nabla_V.  v[d] = UNet output; returns the loss term and writes
+// dv[d]; G row gets -dv.  (method.py:280-287, 692-720)
+__device__ __forceinline__ float point_loss(const LossArgs& a, int i, int m, const float* x, int ldx,
+                                            const float* v, int ldv, float* dv) {
+  const socm_setting& st = a.st;
+  const int d = st.d;
+  float diff[kMaxDim], r[kMaxDim];
+  for (int j = 0; j < d; ++j) diff[j] = v[j * ldv];
+  if (a.warmA != nullptr) {
+    // nabla_V - sigma^{-T} u_ws(t_i, x),  u_ws = sigma^{-1}(c_i + A_i x - b(x))
+    float uws[kMaxDim];
+    for (int j = 0; j < d; ++j) uws[j] = 0.f;
+    add_warm_start(st, a.warmA + (size_t)i * d * d, a.warmc + (size_t)i * d, x, ldx, uws);
+    if (st.sigma_is_identity) {
+      for (int j = 0; j < d; ++j) diff[j] -= uws[j];
+    } else {
+      matvec_t(st.sigma_inv, d, uws, r);
+      for (int j = 0; j < d; ++j) diff[j] -= r[j];
+    }
+  }
+  const float* trow = a.target + (size_t)m * a.ldt + (size_t)i * d;
+  for (int j = 0; j < d; ++j) diff[j] -= __ldg(trow + j);
+  const float s = a.stop ? __ldg(a.stop + (size_t)i * a.B + m) : 1.f;
+  const float coef = s * __ldg(a.w + m) * a.scale;
+  float sq = 0.f;
+  if (st.sigma_is_identity) {
+    for (int j = 0; j < d; ++j) {
+      sq = fmaf(diff[j], diff[j], sq);
+      dv[j] = 2.f * coef * diff[j];
+    }
+  } else {
+    matvec_t(st.sigma, d, diff, r);  // r = sigma^T diff
+    for (int j = 0; j < d; ++j) sq = fmaf(r[j], r[j], sq);
+    float t[kMaxDim];
+    matvec(st.sigma, d, r, t);       // sigma sigma^T diff
+    for (int j = 0; j < d; ++j) dv[j] = 2.f * coef * t[j];
+  }
+  float* grow = a.G + (size_t)m * a.ldt + (size_t)i * d;
+  for (int j = 0; j < d; ++j) grow[j] = -dv[j];
+  return coef * sq;
+}
+
+__global__ void __launch_bounds__(128) loss_generic_kernel(LossArgs a, socm_unet net, float* __restrict__ grad) {
+  extern __shared__ __align__(128) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int d = a.st.d, h0 = net.h0, h1 = net.h1, h2 = net.h2;
+  const int per_warp = generic::fwd_floats(d, h0, h1, h2) + generic::bwd_floats(d, h0, h1, h2);
+  float* base = smem + (size_t)warp * per_warp;
+  generic::FwdBuf b = generic::carve_fwd(base, d, h0, h1, h2);
+  float* bw = base + generic::fwd_floats(d, h0, h1, h2);
+  const generic::GradPtrs g = generic::grad_ptrs(grad, d, h0, h1, h2);
+  const size_t total = (size_t)(a.K + 1) * a.B;
+  double loss_acc = 0.0;
+  for (size_t q = (size_t)blockIdx.x * nwarp + warp; q < total; q += (size_t)gridDim.x * nwarp) {
+    const int i = (int)(q / a.B), m = (int)(q - (size_t)i * a.B);
+    if (lane == 0) b.xin[0] = __ldg(a.ts + i);
+    for (int j = lane; j < d; j += 32) b.xin[1 + j] = __ldg(a.states + ((size_t)i * a.B + m) * d + j);
+    __syncwarp();
+    generic::forward(net, b, lane);
+    if (lane == 0) loss_acc += (double)point_loss(a, i, m, b.xin + 1, 1, b.o0, 1, bw);
+    __syncwarp();
+    generic::backward(net, b, bw, g, lane);
+  }
+  if (lane == 0 && loss_acc != 0.0) atomicAdd(a.loss_sums, loss_acc);
+}
+
+int launch_loss_tile(const LossArgs& a, const socm_unet* net, float* grad, void* workspace, cudaStream_t stream);
+
+}  // namespace socm
+
+// ================================================================ C ABI
+using namespace socm;
+
+extern "C" int64_t socm_loss_workspace_bytes(const socm_unet* net, int32_t B, int32_t K) {
+  if (!net) return -1;
+  (void)B;
+  (void)K;
+  return 256;  // the generic kernel needs no workspace; loss_tile.cu overrides via its own query
+}
+
+extern "C" int socm_unet_loss_fwdbwd_f32(const socm_setting* st, const socm_unet* net, const socm_warm_table* warm,
+                                         const float* ts, const float* states, const float* target, int32_t ldt,
+                                         const float* w, const float* stop, float scale, int32_t B, int32_t K,
+                                         float* G, float* grad, double* loss_sums, void* workspace, uint32_t flags,
+                                         void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = validate_setting(st)) return rc;
+  if (int rc = validate_unet(net, st->d)) return rc;
+  SOCM_CHECK_ARG(ts && states && target && w && G && grad && loss_sums, "required pointer is NULL");
+  SOCM_CHECK_ARG(B >= 0 && K >= 1 && ldt >= (K + 1) * st->d, "bad sizes B=%d K=%d ldt=%d", B, K, ldt);
+  SOCM_CHECK_ARG(!warm || (warm->A && warm->c), "warm-start table has NULL members");
+  if (B == 0) return SOCM_OK;
+  LossArgs a;
+  a.st = *st;
+  a.warmA = warm ? warm->A : nullptr;
+  a.warmc = warm ? warm->c : nullptr;
+  a.ts = ts;
+  a.states = states;
+  a.target = target;
+  a.w = w;
+  a.stop = stop;
+  a.scale = scale;
+  a.B = B;
+  a.K = K;
+  a.ldt = ldt;
+  a.G = G;
+  a.loss_sums = loss_sums;
+  (void)workspace;
+  (void)flags;
+  const int warps = 4;
+  const size_t smem = (size_t)warps *
+                      (generic::fwd_floats(st->d, net->h0, net->h1, net->h2) +
+                       generic::bwd_floats(st->d, net->h0, net->h1, net->h2)) *
+                      sizeof(float);
+  SOCM_CHECK_ARG(smem <= 200 * 1024, "hidden sizes too large for the generic kernel");
+  SOCM_CUDA(cudaFuncSetAttribute(loss_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t total = (size_t)(K + 1) * B;
+  size_t grid = (total + warps - 1) / warps;
+  const size_t cap = (size_t)sm_count() * 8;
+  if (grid > cap) grid = cap;
+  loss_generic_kernel<<<(int)grid, warps * 32, smem, stream>>>(a, *net, grad);
+  SOCM_LAUNCH_CHECK();
+  return SOCM_OK;
+}

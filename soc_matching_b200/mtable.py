@@ -1,0 +1,80 @@
+"""The block upper-triangular table L of the SOCM target.
+
+The reference fills two (K+1, K+1, d, d) tensors with M(t_i, s_j) and d/ds M(t_i, s_j) by a
+Python loop over rows (method.py:517-582) and later contracts them against per-sample
+vectors through a (K+1, K+1, B, d, d) intermediate (method.py:591-631).  Here the same numbers
+are laid out once as the left operand of a GEMM:
+
+    L[(i,k), :] = [ M_i0[k,:]  dM_i0[k,:]  M_i1[k,:]  dM_i1[k,:] ... M_i,K-1  dM_i,K-1  M_iK[k,:] ]
+
+with zero blocks for j < i, so that  target = R L^T  (csrc/target.cu).  Everything in this file
+is torch ops (device-agnostic, differentiable w.r.t. the M-network and gamma); it is
+B-independent and runs once per iteration.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+
+@dataclass
+class PairGrid:
+    """(t, s) pairs with s >= t and the gather map from blocks of L to rows of the pair list."""
+
+    K: int
+    t: torch.Tensor        # (P,)
+    s: torch.Tensor        # (P,)
+    block_index: torch.Tensor  # (K+1, 2K+1) int64 into cat([M_all, dM_all, zero]) rows
+    P: int
+
+
+def make_pair_grid(ts: torch.Tensor, T: float) -> PairGrid:
+    """s values are regenerated per row with linspace exactly like method.py:535-547 (they differ
+    from ts[i:] in the last ulp at some entries), on the CPU in fp32, then moved to ts.device."""
+    K = ts.shape[0] - 1
+    ts_cpu = ts.detach().float().cpu()
+    t_rows, s_rows = [], []
+    for k in range(K + 1):
+        s_rows.append(torch.linspace(ts_cpu[k], T, K + 1 - k))
+        t_rows.append(ts_cpu[k] * torch.ones(K + 1 - k))
+    t_vec, s_vec = torch.cat(t_rows), torch.cat(s_rows)
+    P = t_vec.shape[0]
+    # row offset of pair (i, j>=i) in the concatenated list
+    start = torch.zeros(K + 1, dtype=torch.int64)
+    for k in range(1, K + 1):
+        start[k] = start[k - 1] + (K + 2 - k)
+    zero_row = 2 * P
+    idx = torch.full((K + 1, 2 * K + 1), zero_row, dtype=torch.int64)
+    for i in range(K + 1):
+        j = torch.arange(i, K + 1)
+        rows = start[i] + (j - i)
+        jm = j[j < K]
+        idx[i, 2 * jm] = rows[: jm.shape[0]]            # M_ij
+        idx[i, 2 * jm + 1] = P + rows[: jm.shape[0]]    # dM_ij
+        idx[i, 2 * K] = rows[-1]                        # M_iK
+    dev = ts.device
+    return PairGrid(K, t_vec.to(dev), s_vec.to(dev), idx.to(dev), P)
+
+
+def build_L(m_all: torch.Tensor, dm_all: torch.Tensor, grid: PairGrid, ldr: int) -> torch.Tensor:
+    """(P,d,d) x2 -> L ((K+1)d, ldr) fp32, zero-padded to the row pitch of R."""
+    K, d = grid.K, m_all.shape[-1]
+    zero = torch.zeros(1, d, d, device=m_all.device, dtype=m_all.dtype)
+    blocks = torch.cat([m_all, dm_all, zero], dim=0)[grid.block_index]        # (K+1, 2K+1, d, d)
+    L = blocks.permute(0, 2, 1, 3).reshape((K + 1) * d, (2 * K + 1) * d)
+    if ldr > L.shape[1]:
+        L = torch.nn.functional.pad(L, (0, ldr - L.shape[1]))
+    return L.contiguous()
+
+
+def dense_tables(m_all: torch.Tensor, dm_all: torch.Tensor, K: int):
+    """Per-sample variant (stopping times): (P, B, d, d) -> two (K+1, K+1, B, d, d) tables, zero
+    for j < i (method.py:502-507, 556-564)."""
+    P, B, d, _ = m_all.shape
+    iu = torch.triu_indices(K + 1, K + 1, device=m_all.device)
+    M = torch.zeros(K + 1, K + 1, B, d, d, device=m_all.device, dtype=m_all.dtype)
+    dM = torch.zeros_like(M)
+    M = M.index_put((iu[0], iu[1]), m_all)
+    dM = dM.index_put((iu[0], iu[1]), dm_all)
+    return M, dM

@@ -1,0 +1,237 @@
+"""Drop-in for the reference's ``SOC_Solver`` (method.py:146-906) restricted to the hot path:
+``loss(..., algorithm in {"SOCM", "SOCM_const_M"})`` returns the same 8-tuple, and
+``objective.backward()`` leaves ``.grad`` on ``neural_sde.nabla_V.parameters()``,
+``neural_sde.M.sigmoid_layers.parameters()`` and ``neural_sde.gamma`` (``gamma2``).
+
+One iteration is: K1 rollout -> R, w (prep) -> L from the M-network (torch, B-independent)
+-> target = R L^T (K2) -> fused UNet forward + weighted loss + backward (K3, produces the
+UNet gradients and G = d loss / d target) -> dL = G^T R (K2 backward) -> torch autograd through
+L into the M-network.  Trajectories are processed in chunks of ``chunk_paths`` so that the
+working set stays bounded for B up to 2^20 and beyond; every kernel accumulates.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib, mtable, networks, simulate
+from .sde import describe_setting
+
+
+class _FusedObjective(torch.autograd.Function):
+    """The kernels have already produced the loss value and all first-order gradients; this node
+    only hands them to autograd (scaled by the incoming gradient, e.g. 1/normalization_const,
+    main.py:320)."""
+
+    @staticmethod
+    def forward(ctx, value, lead, lead_grad, unet_grad_flat, *unet_params):
+        ctx.save_for_backward(lead_grad if lead_grad is not None else value.new_zeros(()), unet_grad_flat)
+        ctx.has_lead = lead is not None and lead_grad is not None
+        ctx.shapes = [p.shape for p in unet_params]
+        return value.clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        lead_grad, flat = ctx.saved_tensors
+        grads, off = [], 0
+        for shp in ctx.shapes:
+            n = math.prod(shp)
+            grads.append((flat[off:off + n] * gout).reshape(shp))
+            off += n
+        return (None, lead_grad * gout if ctx.has_lead else None, None, None, *grads)
+
+
+class SOC_Solver(nn.Module):
+    noise_type = "diagonal"
+    sde_type = "ito"
+
+    def __init__(self, neural_sde, x0, ut, T=1.0, num_steps=100, lmbd=1.0, d=2, sigma=None):
+        super().__init__()
+        self.dim = neural_sde.dim
+        self.neural_sde = neural_sde
+        self.x0, self.ut, self.T = x0, ut, T
+        self.ts = torch.linspace(0, T, num_steps + 1).to(x0.device)   # method.py:167
+        self.num_steps = num_steps
+        self.dt = T / num_steps
+        self.lmbd, self.d = lmbd, d
+        self.y0 = nn.Parameter(torch.randn(1, device=x0.device))       # method.py:172 (unused by SOCM)
+        self.sigma = neural_sde.sigma if sigma is None else sigma
+        self.chunk_paths = 1 << 16
+        self.force_generic = False          # tests: run the shape-generic kernels
+        self._injected_noise = None         # tests: (K, B, d) noise replayed by the next loss() call
+        self._pair_grid = None
+
+    # ------------------------------------------------------------------ helpers
+    def inject_noise(self, noises: Optional[torch.Tensor]):
+        """Parity hook: the next ``loss`` call uses these Brownian increments instead of Philox."""
+        self._injected_noise = noises
+
+    def control(self, t0, x0):
+        """method.py:175-183."""
+        x0 = x0.reshape(-1, self.dim)
+        tx = torch.cat([t0.reshape(-1, 1).expand(x0.shape[0], 1), x0], dim=-1)
+        return -torch.einsum("ij,bj->bi", self.sigma.t(), self.neural_sde.nabla_V(tx))
+
+    def control_objective(self, batch_size, total_n_samples=65536):
+        """method.py:185-221 (returns the trajectories of the first batch as the third item)."""
+        mean, err = simulate.control_objective(self.neural_sde, self.x0, self.ts, self.lmbd, batch_size,
+                                               total_n_samples)
+        first = simulate.stochastic_trajectories(self.neural_sde, self.x0.repeat(batch_size, 1), self.ts,
+                                                 self.lmbd)[0]
+        return mean, err, first
+
+    def _grid(self):
+        if self._pair_grid is None or self._pair_grid.t.device != self.ts.device:
+            self._pair_grid = mtable.make_pair_grid(self.ts, self.T)
+        return self._pair_grid
+
+    # ------------------------------------------------------------------ the hot path
+    def loss(self, batch_size, compute_L2_error=False, optimal_control=None, compute_control_objective=False,
+             algorithm="SOCM_const_M", add_weights=False, total_n_samples=65536, verbose=False,
+             u_warm_start=None, use_warm_start=True, use_stopping_time=False):
+        if algorithm not in ("SOCM", "SOCM_const_M"):
+            raise NotImplementedError(
+                f"algorithm {algorithm!r}: only SOCM and SOCM_const_M are on the B200 hot path "
+                "(SURVEY.md section 8; the other losses are 'next' rows)")
+        if compute_L2_error:
+            raise NotImplementedError("compute_L2_error needs the tabulated ground-truth controls (section 8f)")
+        lib = _lib.load()
+        sde = self.neural_sde
+        dev = self.x0.device
+        _lib.require_cuda(self.x0, "x0")
+        desc = describe_setting(sde, dev)
+        desc.c_struct.lmbd = float(self.lmbd)
+        d, K, B = desc.d, self.num_steps, int(batch_size)
+        ts = self.ts.to(dev)
+        stopping = bool(use_stopping_time)
+        if stopping and not desc.has_stopping:
+            raise _lib.SocmError("use_stopping_time=True needs a setting with a stopping function Phi")
+        # warm start: the reference only applies it in the loss if u_warm_start is passed AND
+        # use_warm_start (method.py:280); the rollout uses the sde's own flags (method.py:77).
+        warm_loss = None
+        if u_warm_start and use_warm_start:
+            warm_loss = simulate.resolve_warm_start(_WarmView(u_warm_start), ts)
+
+        unet = sde.nabla_V
+        udesc, keep = networks.unet_desc(unet)
+        uparams = networks.unet_parameters(unet)
+        n_par = int(lib.socm_unet_param_count(udesc))
+        f32 = dict(device=dev, dtype=torch.float32)
+        grad_flat = torch.zeros(n_par, **f32)
+        loss_sum = torch.zeros(1, device=dev, dtype=torch.float64)
+        stats = torch.zeros(3, device=dev, dtype=torch.float64)
+        ldt = ((K + 1) * d + 3) // 4 * 4
+        ldr = ((2 * K + 1) * d + 3) // 4 * 4
+        nrows = (K + 1) * d
+        stream = _lib.stream_ptr()
+
+        # ---- B-independent part: the M table (SOCM without stopping times)
+        L = dL = None
+        m_all = dm_all = None
+        if algorithm == "SOCM" and not stopping:
+            grid = self._grid()
+            m_all, dm_all = sde.M.value_and_ds(grid.t, grid.s)
+            L = mtable.build_L(m_all, dm_all, grid, ldr)
+            dL = torch.zeros(nrows, ldr, **f32)
+
+        chunk = min(B, int(self.chunk_paths))
+        wsp = simulate.RolloutWorkspace(desc, unet, chunk, K, dev, True)
+        R = torch.empty(chunk, ldr, **f32)
+        wbuf = torch.empty(chunk, **f32)
+        target = torch.empty(chunk, ldt, **f32)
+        G = torch.zeros(chunk, ldt, **f32)
+        lws = int(lib.socm_loss_workspace_bytes(udesc, chunk, K))
+        loss_ws = torch.empty((lws + 3) // 4, **f32)
+        stop_all = []
+        seed = simulate.next_seed()
+        scale = 1.0 if stopping else 1.0 / ((K + 1) * B)                    # method.py:715 / 720
+        warm_struct = simulate._warm_struct(warm_loss.A_loss, warm_loss.c_loss) if warm_loss is not None else None
+        target_graph = None   # stopping case: the torch-side target (keeps the autograd graph)
+        if stopping and B > chunk:
+            raise NotImplementedError("stopping-time SOCM is not chunked yet: batch_size must be <= chunk_paths")
+
+        x0_rep = self.x0.detach().float().reshape(1, d)
+        for start in range(0, B, chunk):
+            nb = min(chunk, B - start)
+            if nb != wsp.B:   # ragged last chunk
+                wsp = simulate.RolloutWorkspace(desc, unet, nb, K, dev, True)
+                R, wbuf = R[:nb], wbuf[:nb]
+                target, G = target[:nb], G[:nb]
+            noises = None
+            if self._injected_noise is not None:
+                noises = self._injected_noise[:, start:start + nb].contiguous()
+            simulate.rollout(sde, x0_rep.expand(nb, d).contiguous(), ts, self.lmbd, noises=noises, seed=seed,
+                             path_offset=start + getattr(self, "path_offset", 0), desc=desc, workspace=wsp,
+                             force_generic=self.force_generic)
+            _lib.check(lib.socm_target_prep_f32(
+                desc.c_struct, _lib.ptr(wsp.states), _lib.ptr(wsp.noises), _lib.ptr(wsp.controls),
+                _lib.ptr(wsp.eff_dt), wsp.lw[0].data_ptr(), wsp.lw[1].data_ptr(), wsp.lw[2].data_ptr(), nb, K,
+                _lib.ptr(R), ldr, _lib.ptr(wbuf), stream))
+            _lib.check(lib.socm_weight_stats_f32(_lib.ptr(wbuf), _lib.ptr(wsp.stop) if stopping else None, nb, K,
+                                                 _lib.ptr(stats), stream))
+            if algorithm == "SOCM_const_M":
+                _lib.check(lib.socm_target_const_m_f32(_lib.ptr(R), nb, K, d, ldr, _lib.ptr(target), ldt, stream))
+            elif not stopping:
+                _lib.check(lib.socm_target_gemm_f32(_lib.ptr(L.detach()), _lib.ptr(R), nb, K, d, ldr,
+                                                    _lib.ptr(target), ldt, stream))
+            else:
+                target_graph = self._stopping_target(sde, wsp, R, ts, K, d, nb)
+                target[:, :nrows].copy_(target_graph.detach())
+            _lib.check(lib.socm_unet_loss_fwdbwd_f32(
+                desc.c_struct, udesc, warm_struct, _lib.ptr(ts.float().contiguous()), _lib.ptr(wsp.states),
+                _lib.ptr(target), ldt, _lib.ptr(wbuf), _lib.ptr(wsp.stop) if stopping else None, scale, nb, K,
+                _lib.ptr(G), _lib.ptr(grad_flat), _lib.ptr(loss_sum), _lib.ptr(loss_ws),
+                _lib.LOSS_FORCE_GENERIC if self.force_generic else 0, stream))
+            if L is not None:
+                _lib.check(lib.socm_target_gemm_bwd_f32(_lib.ptr(G), _lib.ptr(R), nb, K, d, ldr, ldt,
+                                                        _lib.ptr(dL), 1, stream))
+            stop_all.append(wsp.stop if B <= chunk else wsp.stop.clone())
+        self._injected_noise = None
+        del keep
+
+        value = loss_sum[0]
+        lead, lead_grad = L, dL
+        if stopping:
+            z = stats[2]                                                   # sum(stop_indicators), method.py:715
+            value = value / z
+            grad_flat = (grad_flat.double() / z).float()
+            lead, lead_grad = target_graph, (G[:, :nrows].double() / z).float()
+        objective = _FusedObjective.apply(value.float(), lead, lead_grad, grad_flat, *uparams)
+
+        mean_w = (stats[0] / B).float()
+        var_w = (stats[1] - stats[0] * stats[0] / B) / max(B - 1, 1)       # unbiased, method.py:904
+        std_w = torch.sqrt(torch.clamp(var_w, min=0.0)).float()
+        stop_indicators = stop_all[0] if len(stop_all) == 1 else torch.cat(stop_all, dim=1)
+
+        ctrl_mean = ctrl_err = trajectory = None
+        if compute_control_objective:
+            ctrl_mean, ctrl_err, trajectory = self.control_objective(batch_size, total_n_samples=total_n_samples)
+        return (objective, None, ctrl_mean, ctrl_err, trajectory, mean_w, std_w, stop_indicators)
+
+    # ------------------------------------------------------------------ stopping-time target (torch side)
+    def _stopping_target(self, sde, wsp, R, ts, K, d, nb):
+        """Per-sample M(t, s, tau) (method.py:484-507, 524-564, 584-690): the table depends on the
+        path through its stopping index, so the contraction is a batched (per path) triangular
+        mat-vec, done with torch ops on the GPU (d = 1 in the reference's setting)."""
+        grid = self._grid()
+        alive_cnt = (wsp.states[..., 0] < 0).to(torch.int32).sum(dim=0)     # Phi(x) = -x_0 > 0
+        tau = (alive_cnt - 1).to(torch.float32) / K                         # method.py:524-530
+        tau_vec = tau.unsqueeze(0).expand(grid.P, nb)
+        m_all, dm_all = sde.M.value_and_ds(grid.t, grid.s, tau_vec)
+        M, dM = mtable.dense_tables(m_all, dm_all, K)
+        Rv = R[:, : (2 * K + 1) * d]
+        ac = Rv[:, : 2 * K * d].reshape(nb, K, 2, d)
+        a, c, gg = ac[:, :, 0], ac[:, :, 1], Rv[:, 2 * K * d:]
+        tgt = (torch.einsum("ijmkl,mjl->mik", M[:, :-1], a) + torch.einsum("ijmkl,mjl->mik", dM[:, :-1], c)
+               + torch.einsum("imkl,ml->mik", M[:, -1], gg))
+        return tgt.reshape(nb, (K + 1) * d)
+
+
+class _WarmView:
+    """Lets ``resolve_warm_start`` treat an explicitly passed u_warm_start like an sde attribute."""
+
+    def __init__(self, ws):
+        self.u_warm_start, self.use_warm_start = ws, True

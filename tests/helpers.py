@@ -111,3 +111,50 @@ class Golden:
 
     def scalar(self, key):
         return float(self.z[key])
+
+
+# ---------------------------------------------------------------------------------------------
+# product-side builders (GPU tests)
+def make_product_sde(setting: "orc.Setting", unet: dict, mnet: dict, gammas: dict, hdims, hdims_M, device,
+                     stopping=False, warm=None):
+    """soc_matching_b200 SDE object carrying the given constants / parameters."""
+    import soc_matching_b200 as sb
+    st = setting
+    dv = lambda t: None if t is None else t.to(device)  # noqa: E731
+    common = dict(device=device, dim=st.d, hdims=hdims, hdims_M=hdims_M, lmbd=st.lmbd, sigma=dv(st.sigma),
+                  gamma=float(gammas["gamma"]))
+    if st.kind == "ou_quadratic":
+        sde = sb.OU_Quadratic(A=dv(st.A), P=dv(st.P), Q=dv(st.Q), **common)
+    elif st.kind == "ou_linear":
+        sde = sb.OU_Linear(A=dv(st.A), omega=dv(st.omega), **common)
+    elif st.kind == "double_well":
+        sde = sb.DoubleWell(kappa=dv(st.kappa), nu=dv(st.nu), **common)
+    else:
+        sde = sb.MolecularDynamics(kappa=dv(st.kappa), use_stopping_time=stopping, gamma2=float(gammas["gamma2"]),
+                                   gamma3=float(gammas["gamma3"]), **common)
+    sde.initialize_models()
+    sde.nabla_V.load_state_dict({k: v.to(device) for k, v in unet.items()})
+    sde.M.sigmoid_layers.load_state_dict(
+        {k[len("sigmoid_layers."):]: v.to(device) for k, v in mnet.items() if k.startswith("sigmoid_layers")})
+    if warm is not None:
+        sde.u_warm_start = sb.WarmStartTable(warm.A_roll, warm.c_roll, warm.A_loss, warm.c_loss).to(device)
+        sde.use_warm_start = True
+    return sde
+
+
+def random_setting(kind: str, d: int, seed: int, lmbd: float = 1.0, dense_sigma: bool = False) -> "orc.Setting":
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, generator=g)  # noqa: E731
+    eye = torch.eye(d)
+    sigma = eye + 0.1 * rn(d, d) if dense_sigma else eye.clone()
+    if kind == "ou_quadratic":
+        return orc.Setting(kind, d, sigma, lmbd, A=0.2 * eye + 0.05 * rn(d, d), P=0.2 * eye + 0.05 * rn(d, d),
+                           Q=0.1 * eye + 0.05 * rn(d, d))
+    if kind == "ou_linear":
+        xi = 0.1 * rn(d, d)
+        return orc.Setting(kind, d, eye + xi, lmbd, A=-eye + xi, omega=torch.ones(d))
+    kappa, nu = torch.ones(d), torch.ones(d)
+    kappa[:3], nu[:3] = 5, 3
+    if kind == "double_well":
+        return orc.Setting(kind, d, sigma, lmbd, kappa=kappa, nu=nu)
+    return orc.Setting(kind, d, eye.clone(), lmbd, kappa=torch.ones(d))

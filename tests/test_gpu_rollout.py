@@ -1,0 +1,169 @@
+"""GPU parity of K1 (csrc/rollout.cu) through the public drop-in ``stochastic_trajectories``:
+against the reference's own outputs (tests/golden), against the oracle at the default network
+width, plus Philox / sharding / edge-case properties.  Tolerances are norm-wise:
+trajectories <= 1e-5, log-weights <= 1e-4 relative, stopping indicators bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import (Golden, golden_names, make_product_sde, orc, random_setting, rel_l2, seeded_mnet,
+                     seeded_unet)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+NAMES = ["states", "noises", "stop_indicators", "fractional_timesteps", "logw_det", "logw_sto", "logw_term",
+         "controls"]
+
+
+def compare_rollout(got, want, tol_state=1e-5, tol_w=1e-4, exact_stop=True):
+    for key, a, b in zip(NAMES, got, want):
+        a = a.detach().float().cpu()
+        b = b.detach().float().cpu()
+        assert a.shape == b.shape, (key, a.shape, b.shape)
+        if key == "stop_indicators" and exact_stop:
+            assert torch.equal(a, b), f"{key}: {int((a != b).sum())} mismatching indicators"
+        elif key.startswith("logw"):
+            assert rel_l2(a, b) <= tol_w, (key, rel_l2(a, b))
+        else:
+            assert rel_l2(a, b) <= tol_state, (key, rel_l2(a, b))
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_rollout_matches_reference_golden(name):
+    import soc_matching_b200 as sb
+    g = Golden(name)
+    sde = make_product_sde(g.setting, g.unet, g.mnet, g.gammas, g.meta["hdims"], g.meta["hdims_M"], DEV,
+                           stopping=g.meta["stopping"], warm=g.warm)
+    x0 = g.x0.to(DEV).repeat(g.meta["B"], 1)
+    out = sb.stochastic_trajectories(sde, x0, g.ts.to(DEV), g.meta["lmbd"], noises=g.traj[1].to(DEV))
+    compare_rollout(out, g.traj)
+    if g.meta["hdims"] == [256, 128, 64]:  # also the shape-generic kernel on the full-width net
+        out2 = sb.stochastic_trajectories(sde, x0, g.ts.to(DEV), g.meta["lmbd"], noises=g.traj[1].to(DEV),
+                                          force_generic=True)
+        compare_rollout(out2, g.traj)
+
+
+CASES = [  # kind, d, K, B, lmbd, dense sigma
+    ("double_well", 10, 40, 100, 1.0, False),
+    ("ou_quadratic", 20, 25, 70, 1.0, False),
+    ("ou_quadratic", 5, 20, 64, 0.5, True),
+    ("ou_linear", 10, 30, 65, 1.0, True),
+    ("molecular_dynamics", 1, 150, 200, 1.0, False),
+    ("double_well", 32, 10, 3, 2.0, True),
+]
+
+
+@pytest.mark.parametrize("kind,d,K,B,lmbd,dense", CASES)
+@pytest.mark.parametrize("generic", [False, True])
+def test_rollout_default_width_matches_oracle(kind, d, K, B, lmbd, dense, generic):
+    import soc_matching_b200 as sb
+    st = random_setting(kind, d, seed=d * 7 + K, lmbd=lmbd, dense_sigma=dense)
+    hd, hm = [256, 128, 64], [32, 32]
+    unet = seeded_unet(d, hd, 11 + d, 0.5 if kind == "molecular_dynamics" else 1.0)
+    mnet = seeded_mnet(d, hm, 12 + d, 0.1, 3 if kind == "molecular_dynamics" else 2)
+    gam = {"gamma": torch.tensor([2.0]), "gamma2": torch.tensor([1.0]), "gamma3": torch.tensor([1.0])}
+    x0 = {"molecular_dynamics": -torch.ones(d), "double_well": torch.zeros(d)}.get(kind, 0.3 * torch.ones(d))
+    ts = torch.linspace(0, 1.0, K + 1)
+    gen = torch.Generator().manual_seed(99)
+    noises = torch.randn(K, B, d, generator=gen)
+    torch.set_num_threads(8)
+    want = orc.rollout(st, unet, x0.repeat(B, 1), ts, noises=noises)
+    sde = make_product_sde(st, unet, mnet, gam, hd, hm, DEV, stopping=(kind == "molecular_dynamics"))
+    got = sb.stochastic_trajectories(sde, x0.to(DEV).repeat(B, 1), ts.to(DEV), lmbd, noises=noises.to(DEV),
+                                     force_generic=generic)
+    if kind == "molecular_dynamics":
+        assert (want[2][-1] == 0).sum() > 5, "test needs stopped paths"
+    compare_rollout(got, want)
+
+
+def test_philox_matches_published_algorithm():
+    from soc_matching_b200 import _lib
+    lib = _lib.load()
+    B, K, d, seed, off = 37, 5, 10, 0x1234567890ABCDEF, 1000
+    out = torch.empty(K, B, d, device=DEV)
+    _lib.check(lib.socm_philox_normal_f32(seed, off, B, K, d, out.data_ptr(), _lib.stream_ptr()))
+    got = out.cpu().numpy()
+    nblk = (d + 3) // 4
+    ctr = np.zeros((K, B, nblk, 4), dtype=np.uint32)
+    ctr[..., 0] = (np.arange(B, dtype=np.uint64) + off).astype(np.uint32)[None, :, None]
+    ctr[..., 1] = ((np.arange(B, dtype=np.uint64) + off) >> np.uint64(32)).astype(np.uint32)[None, :, None]
+    ctr[..., 2] = np.arange(K, dtype=np.uint32)[:, None, None]
+    ctr[..., 3] = np.arange(nblk, dtype=np.uint32)[None, None, :]
+    bits = orc.philox4x32_10(ctr, np.array([seed & 0xFFFFFFFF, seed >> 32], dtype=np.uint64))
+    u = (bits.astype(np.float64) + 0.5) * 2.0**-32
+    r0, r1 = np.sqrt(-2 * np.log(u[..., 0])), np.sqrt(-2 * np.log(u[..., 2]))
+    z = np.stack([r0 * np.cos(2 * np.pi * u[..., 1]), r0 * np.sin(2 * np.pi * u[..., 1]),
+                  r1 * np.cos(2 * np.pi * u[..., 3]), r1 * np.sin(2 * np.pi * u[..., 3])], axis=-1)
+    want = z.reshape(K, B, nblk * 4)[:, :, :d]
+    assert np.abs(got - want).max() < 5e-6
+    big = torch.empty(64, 4096, 8, device=DEV)
+    _lib.check(lib.socm_philox_normal_f32(7, 0, 4096, 64, 8, big.data_ptr(), _lib.stream_ptr()))
+    assert abs(float(big.mean())) < 3e-3 and abs(float(big.std()) - 1) < 3e-3
+    assert abs(float((big**4).mean()) - 3.0) < 0.05
+
+
+def _dw_sde(d=10, seed=5):
+    st = random_setting("double_well", d, seed=3)
+    gam = {"gamma": torch.tensor([6.0]), "gamma2": torch.tensor([1.0]), "gamma3": torch.tensor([1.0])}
+    return make_product_sde(st, seeded_unet(d, [256, 128, 64], seed), seeded_mnet(d, [128, 128], seed + 1), gam,
+                            [256, 128, 64], [128, 128], DEV)
+
+
+def test_philox_rollout_is_sharding_invariant_and_deterministic():
+    from soc_matching_b200 import simulate
+    sde = _dw_sde()
+    ts = torch.linspace(0, 1.0, 41, device=DEV)
+    x0 = torch.zeros(300, 10, device=DEV)
+    full = simulate.rollout(sde, x0, ts, 1.0, seed=42)
+    again = simulate.rollout(sde, x0, ts, 1.0, seed=42)
+    assert torch.equal(full.states, again.states) and torch.equal(full.lw, again.lw)
+    part = simulate.rollout(sde, x0[:130], ts, 1.0, seed=42, path_offset=170)
+    assert torch.equal(part.states, full.states[:, 170:]) and torch.equal(part.noises, full.noises[:, 170:])
+    assert torch.equal(part.lw, full.lw[:, 170:])
+    other = simulate.rollout(sde, x0, ts, 1.0, seed=43)
+    assert not torch.equal(other.noises, full.noises)
+    # the drawn noise is what socm_philox_normal_f32 returns, and replaying it reproduces the run
+    replay = simulate.rollout(sde, x0, ts, 1.0, noises=full.noises.clone())
+    assert torch.equal(replay.states, full.states)
+
+
+def test_weights_only_mode_matches_full_mode():
+    from soc_matching_b200 import simulate
+    sde = _dw_sde()
+    ts = torch.linspace(0, 1.0, 31, device=DEV)
+    x0 = torch.zeros(129, 10, device=DEV)
+    a = simulate.rollout(sde, x0, ts, 1.0, seed=9)
+    b = simulate.rollout(sde, x0, ts, 1.0, seed=9, store_traj=False)
+    assert b.states is None and torch.equal(a.lw, b.lw)
+
+
+def test_edge_cases():
+    import soc_matching_b200 as sb
+    sde = _dw_sde()
+    ts = torch.linspace(0, 1.0, 3, device=DEV)
+    out = sb.stochastic_trajectories(sde, torch.zeros(0, 10, device=DEV), ts, 1.0)      # empty batch
+    assert out[0].shape == (3, 0, 10)
+    out = sb.stochastic_trajectories(sde, torch.zeros(1, 10, device=DEV), torch.linspace(0, 1, 2, device=DEV), 1.0)
+    assert out[0].shape == (2, 1, 10) and torch.isfinite(out[0]).all()                 # B = 1, K = 1
+    with pytest.raises(NotImplementedError):
+        sb.stochastic_trajectories(sde, torch.zeros(2, 10, device=DEV), ts, 1.0, detach=False)
+    sde.use_learned_control = False
+    with pytest.raises(NotImplementedError):
+        sb.stochastic_trajectories(sde, torch.zeros(2, 10, device=DEV), ts, 1.0)
+
+
+def test_full_size_rollout_properties():
+    """BASELINE config 5 at full size (double_well d=10, K=200, B=2^20): any 64-path slice of the
+    big run equals the same paths rolled out on their own (path-indexed Philox), all values finite."""
+    from soc_matching_b200 import simulate
+    sde = _dw_sde()
+    K, B = 200, 1 << 20
+    ts = torch.linspace(0, 1.0, K + 1, device=DEV)
+    big = simulate.rollout(sde, torch.zeros(B, 10, device=DEV), ts, 1.0, seed=2024)
+    assert torch.isfinite(big.lw).all() and torch.isfinite(big.states[-1]).all()
+    for m0 in (0, 12345 * 64, B - 64):
+        small = simulate.rollout(sde, torch.zeros(64, 10, device=DEV), ts, 1.0, seed=2024, path_offset=m0)
+        assert torch.equal(small.states, big.states[:, m0:m0 + 64])
+        assert torch.equal(small.lw, big.lw[:, m0:m0 + 64])
+    del big
+    torch.cuda.empty_cache()

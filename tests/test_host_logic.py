@@ -1,0 +1,116 @@
+"""CPU tests of the host-side logic (torch ops, device-agnostic): the M-table layout, the
+forward-mode d/ds M, and the re-association  target = R L^T   against the
+oracle's faithful (K+1,K+1,B,d,d) formulation."""
+import math
+
+import pytest
+import torch
+
+from helpers import Golden, golden_names, orc, rel_l2
+from soc_matching_b200 import mtable, networks, simulate
+
+torch.set_num_threads(1)
+
+
+def cpu_prep(st, traj, K):
+    """Reference semantics of csrc/target.cu:target_prep_kernel in torch (test-only)."""
+    states, noises, _stop, eff, lw_det, lw_sto, lw_term, controls = traj
+    sig_inv_t = torch.inverse(st.sigma).t()
+    c = torch.einsum("ij,abj->abi", sig_inv_t,
+                     math.sqrt(st.lmbd) * torch.sqrt(eff).unsqueeze(2) * noises + eff.unsqueeze(2) * controls)
+    gb = orc.grad_drift(st, states[:-1])
+    a = eff.unsqueeze(2) * orc.grad_run_cost(st, states[:-1]) - torch.einsum("abij,abj->abi", gb, c)
+    B, d = states.shape[1], st.d
+    R = torch.cat([torch.stack([a, c], dim=2).permute(1, 0, 2, 3).reshape(B, 2 * K * d),
+                   orc.grad_term_cost(st, states[-1])], dim=1)
+    return R, torch.exp(lw_det + lw_sto + lw_term)
+
+
+def load_mnet(g, stopping):
+    d = g.meta["d"]
+    gam = {k: torch.nn.Parameter(v.clone()) for k, v in g.gammas.items()}
+    if stopping:
+        m = networks.TwoBoundarySigmoidMLP(d, g.meta["hdims_M"], gam["gamma"], gam["gamma2"], gam["gamma3"])
+    else:
+        m = networks.SigmoidMLP(d, g.meta["hdims_M"], gam["gamma"])
+    sd = {k: v for k, v in g.mnet.items() if k.startswith("sigmoid_layers")}
+    m.sigmoid_layers.load_state_dict({k[len("sigmoid_layers."):]: v for k, v in sd.items()})
+    return m, gam
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "molecular" not in n])
+def test_value_and_ds_matches_jacrev(name):
+    g = Golden(name)
+    m, gam = load_mnet(g, False)
+    grid = mtable.make_pair_grid(g.ts, 1.0)
+    t_ref, s_ref = orc._pair_grid(g.ts, 1.0)
+    assert torch.equal(grid.t, t_ref) and torch.equal(grid.s, s_ref)
+    val, ds = m.value_and_ds(grid.t, grid.s)
+    want = orc.m_apply(g.mnet, g.gammas["gamma"], t_ref, s_ref, g.meta["d"])
+    jac = torch.func.jacrev(lambda t, s: orc.m_apply(g.mnet, g.gammas["gamma"], t, s, g.meta["d"]).sum(0), argnums=1)
+    want_ds = jac(t_ref, s_ref).permute(2, 0, 1)
+    assert rel_l2(val, want) < 1e-6
+    assert rel_l2(ds, want_ds) < 1e-5
+
+
+def test_two_boundary_matches_oracle():
+    g = Golden("c4_molecular_dynamics")
+    m, gam = load_mnet(g, True)
+    K = g.meta["K"]
+    t_ref, s_ref = orc._pair_grid(g.ts, 1.0)
+    tau = (torch.sum((orc.stop_fn(g.setting, g.traj[0]) > 0).to(torch.int), dim=0) - 1) / K
+    tau_vec = tau.unsqueeze(0).expand(t_ref.shape[0], -1)
+    val, ds = m.value_and_ds(t_ref, s_ref, tau_vec)
+    want = orc.m_apply_stopping(g.mnet, g.gammas["gamma"], g.gammas["gamma2"], g.gammas["gamma3"], t_ref, s_ref,
+                                tau_vec, 1)
+    jac = torch.func.jacrev(lambda t, s, tv: orc.m_apply_stopping(
+        g.mnet, g.gammas["gamma"], g.gammas["gamma2"], g.gammas["gamma3"], t, s, tv, 1).sum(0), argnums=1)
+    want_ds = torch.nan_to_num(jac(t_ref, s_ref, tau_vec).permute(3, 0, 1, 2))
+    assert rel_l2(val, want) < 1e-6
+    assert rel_l2(ds, want_ds) < 1e-5
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "molecular" not in n])
+def test_reassociated_target_reproduces_reference_loss_and_grads(name):
+    g = Golden(name)
+    st, K, d, B = g.setting, g.meta["K"], g.meta["d"], g.meta["B"]
+    m, gam = load_mnet(g, False)
+    grid = mtable.make_pair_grid(g.ts, 1.0)
+    R, w = cpu_prep(st, g.traj, K)
+    ldr = ((2 * K + 1) * d + 3) // 4 * 4
+    Rp = torch.nn.functional.pad(R, (0, ldr - R.shape[1]))
+    m_all, dm_all = m.value_and_ds(grid.t, grid.s)
+    L = mtable.build_L(m_all, dm_all, grid, ldr)
+    target = (Rp @ L.t()).reshape(B, K + 1, d).permute(1, 0, 2)
+    unet = {k: v.clone().requires_grad_(True) for k, v in g.unet.items()}
+    gv = orc.nabla_v_all(st, unet, g.ts, g.traj[0], g.warm)
+    diff = torch.einsum("ij,abj->abi", st.sigma.t(), gv - target)
+    obj = torch.sum(diff**2 * w.unsqueeze(0).unsqueeze(2)) / ((K + 1) * B)
+    assert abs(float(obj) - g.scalar("SOCM/loss")) <= 5e-6 * abs(g.scalar("SOCM/loss"))
+    obj.backward()
+    ref = g.grads("SOCM")
+    for key, want in ref.items():
+        grp, pname = key.split("/", 1)
+        if grp == "unet":
+            got = unet[pname].grad
+        elif grp == "gam":
+            got = gam[pname].grad
+        else:
+            got = dict(m.named_parameters())[pname].grad
+        got = torch.zeros_like(want) if got is None else got
+        assert rel_l2(got, want) <= 5e-5, (key, rel_l2(got, want))
+
+
+def test_step_table_matches_reference_scalars():
+    ts = torch.linspace(0, 1.0, 201)
+    tab = simulate.step_table(ts, 0.7)
+    for k in (0, 17, 199):
+        dt = ts[k + 1] - ts[k]
+        assert tab[0, k] == dt and tab[1, k] == torch.sqrt(0.7 * dt)
+        assert tab[2, k] == dt / 0.7 and tab[3, k] == torch.sqrt(dt / 0.7) and tab[4, k] == ts[k]
+
+
+def test_warm_table_wrapper_roundtrip():
+    g = Golden("c3_ou_quadratic_hard_warm")
+    tbl = networks.WarmStartTable(g.warm.A_roll, g.warm.c_roll, g.warm.A_loss, g.warm.c_loss)
+    assert bool(tbl) and tbl.A_roll.shape == (g.meta["K"], 3, 3) and tbl.A_loss.shape == (g.meta["K"] + 1, 3, 3)
