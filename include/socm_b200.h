@@ -139,7 +139,8 @@ int socm_target_const_m_f32(const float* R, int32_t B, int32_t K, int32_t d, int
  * G[B][ldt]     = d loss / d target  (same scale);  grad[...] += d loss / d UNet parameters,
  * flat in the layer order of socm_unet (w then b per layer).
  * stop may be NULL (all ones).  warm: rows = K+1 (rank-3 branch, models.py:184-186) or NULL.
- * workspace: socm_loss_workspace_bytes() bytes. */
+ * workspace: socm_loss_workspace_bytes() bytes.  flags: SOCM_LOSS_FORCE_GENERIC. */
+#define SOCM_LOSS_FORCE_GENERIC 1u
 int64_t socm_loss_workspace_bytes(const socm_unet* net, int32_t B, int32_t K);
 int64_t socm_unet_param_count(const socm_unet* net);
 int socm_unet_loss_fwdbwd_f32(const socm_setting* st, const socm_unet* net, const socm_warm_table* warm,

@@ -44,7 +44,7 @@ def main():
                                                        force_generic=True), warm=1, reps=2)
             print(f"rollout generic B={B:7d} K={K}: {best*1e3:9.3f} ms  {B*K/best:.3e} traj-steps/s")
     solver = sb.SOC_Solver(sde, x0, None, T=1.0, num_steps=K, lmbd=1.0, d=d, sigma=sigma)
-    for B in (128, 1024):
+    for B in (128, 1024, 148 * 64, 1 << 16):
         def it():
             for p in sde.parameters():
                 p.grad = None

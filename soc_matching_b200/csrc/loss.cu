@@ -6,66 +6,10 @@
 //   loss_generic_kernel  one warp per point, any hdims; parameter gradients by global atomics
 //   (the tiled kernel for the default hdims lives in loss_tile.cu)
 #include "kernels.h"
+#include "loss_common.cuh"
 #include "unet_generic.cuh"
 
 namespace socm {
-
-struct LossArgs {
-  socm_setting st;
-  const float* warmA;  // [K+1][d][d] or NULL
-  const float* warmc;  // [K+1][d]
-  const float* ts;     // [K+1]
-  const float* states; // [K+1][B][d]
-  const float* target; // [B][ldt]
-  const float* w;      // [B]
-  const float* stop;   // [K+1][B] or NULL
-  float scale;
-  int B, K, ldt;
-  float* G;            // [B][ldt]
-  double* loss_sums;
-};
-
-// Per-point loss and d loss / d nabla_V.  v[d] = UNet output; returns the loss term and writes
-// dv[d]; G row gets -dv.  (method.py:280-287, 692-720)
-__device__ __forceinline__ float point_loss(const LossArgs& a, int i, int m, const float* x, int ldx,
-                                            const float* v, int ldv, float* dv) {
-  const socm_setting& st = a.st;
-  const int d = st.d;
-  float diff[kMaxDim], r[kMaxDim];
-  for (int j = 0; j < d; ++j) diff[j] = v[j * ldv];
-  if (a.warmA != nullptr) {
-    // nabla_V - sigma^{-T} u_ws(t_i, x),  u_ws = sigma^{-1}(c_i + A_i x - b(x))
-    float uws[kMaxDim];
-    for (int j = 0; j < d; ++j) uws[j] = 0.f;
-    add_warm_start(st, a.warmA + (size_t)i * d * d, a.warmc + (size_t)i * d, x, ldx, uws);
-    if (st.sigma_is_identity) {
-      for (int j = 0; j < d; ++j) diff[j] -= uws[j];
-    } else {
-      matvec_t(st.sigma_inv, d, uws, r);
-      for (int j = 0; j < d; ++j) diff[j] -= r[j];
-    }
-  }
-  const float* trow = a.target + (size_t)m * a.ldt + (size_t)i * d;
-  for (int j = 0; j < d; ++j) diff[j] -= __ldg(trow + j);
-  const float s = a.stop ? __ldg(a.stop + (size_t)i * a.B + m) : 1.f;
-  const float coef = s * __ldg(a.w + m) * a.scale;
-  float sq = 0.f;
-  if (st.sigma_is_identity) {
-    for (int j = 0; j < d; ++j) {
-      sq = fmaf(diff[j], diff[j], sq);
-      dv[j] = 2.f * coef * diff[j];
-    }
-  } else {
-    matvec_t(st.sigma, d, diff, r);  // r = sigma^T diff
-    for (int j = 0; j < d; ++j) sq = fmaf(r[j], r[j], sq);
-    float t[kMaxDim];
-    matvec(st.sigma, d, r, t);       // sigma sigma^T diff
-    for (int j = 0; j < d; ++j) dv[j] = 2.f * coef * t[j];
-  }
-  float* grow = a.G + (size_t)m * a.ldt + (size_t)i * d;
-  for (int j = 0; j < d; ++j) grow[j] = -dv[j];
-  return coef * sq;
-}
 
 __global__ void __launch_bounds__(128) loss_generic_kernel(LossArgs a, socm_unet net, float* __restrict__ grad) {
   extern __shared__ __align__(128) float smem[];
@@ -92,6 +36,7 @@ __global__ void __launch_bounds__(128) loss_generic_kernel(LossArgs a, socm_unet
 }
 
 int launch_loss_tile(const LossArgs& a, const socm_unet* net, float* grad, void* workspace, cudaStream_t stream);
+int64_t loss_tile_workspace_bytes(int d, int B, int K);
 
 }  // namespace socm
 
@@ -100,9 +45,8 @@ using namespace socm;
 
 extern "C" int64_t socm_loss_workspace_bytes(const socm_unet* net, int32_t B, int32_t K) {
   if (!net) return -1;
-  (void)B;
-  (void)K;
-  return 256;  // the generic kernel needs no workspace; loss_tile.cu overrides via its own query
+  if (is_default_arch(net)) return loss_tile_workspace_bytes(net->d, B, K);
+  return 256;  // the generic kernel needs no workspace
 }
 
 extern "C" int socm_unet_loss_fwdbwd_f32(const socm_setting* st, const socm_unet* net, const socm_warm_table* warm,
@@ -132,8 +76,7 @@ extern "C" int socm_unet_loss_fwdbwd_f32(const socm_setting* st, const socm_unet
   a.ldt = ldt;
   a.G = G;
   a.loss_sums = loss_sums;
-  (void)workspace;
-  (void)flags;
+  if (is_default_arch(net) && !(flags & 1u)) return launch_loss_tile(a, net, grad, workspace, stream);
   const int warps = 4;
   const size_t smem = (size_t)warps *
                       (generic::fwd_floats(st->d, net->h0, net->h1, net->h2) +

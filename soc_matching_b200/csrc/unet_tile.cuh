@@ -34,13 +34,13 @@ static_assert(FT_FLOATS % CHUNK == 0, "tape must be whole chunks");
 
 // ---- backward tape: W ([n][k], native nn.Linear layout = contraction-major for dgrad) in the
 // order the backward pass consumes them (see loss_tile.cu)
-constexpr int BT_U1 = 0;                    // up_1  [256][128]   d_o2  = W^T d_y1
-constexpr int BT_R1 = BT_U1 + H0 * H1;      // res_1 [256][256]   d_r1  = W^T d_o1
-constexpr int BT_U2 = BT_R1 + H0 * H0;      // up_2  [128][64]    d_r3  = W^T d_y2
-constexpr int BT_R2 = BT_U2 + H1 * H2;      // res_2 [128][128]   d_r2  = W^T d_o2
+constexpr int BT_U1 = 0;                    // up_1   [256][128]  d_o2  = W^T d_y1
+constexpr int BT_U2 = BT_U1 + H0 * H1;      // up_2   [128][64]   d_r3  = W^T d_y2
+constexpr int BT_R2 = BT_U2 + H1 * H2;      // res_2  [128][128]  d_r2  = W^T d_o2
 constexpr int BT_D2 = BT_R2 + H1 * H1;      // down_2 [64][128]   d_r2 += W^T d_z3
-constexpr int BT_D1 = BT_D2 + H2 * H1;      // down_1 [128][256]  d_r1 += W^T d_z2
-constexpr int BT_FLOATS = BT_D1 + H1 * H0;  // 163 840
+constexpr int BT_D1 = BT_D2 + H2 * H1;      // down_1 [128][256]  d_r1  = W^T d_z2
+constexpr int BT_R1 = BT_D1 + H1 * H0;      // res_1  [256][256]  d_r1 += W^T d_o1
+constexpr int BT_FLOATS = BT_R1 + H0 * H0;  // 163 840
 constexpr int BT_CHUNKS = BT_FLOATS / CHUNK;
 static_assert(BT_FLOATS == FT_FLOATS, "same weights");
 
@@ -299,6 +299,25 @@ __device__ __forceinline__ void load_tile(TileAcc<N>& acc, const float* Y, const
   }
 }
 
+// Spill a register tile to this CTA's global scratch, compact feature-major [feat][BT]
+// (activations needed again by the backward pass do not fit shared memory).
+template <int N>
+__device__ __forceinline__ void spill_acc(const TileAcc<N>& acc, float* __restrict__ S, const Coord& co) {
+#pragma unroll
+  for (int j = 0; j < TileAcc<N>::TN; ++j) {
+    float* row = S + co.feat<N>(j) * BT + co.pA;
+    __stcg(reinterpret_cast<float4*>(row), make_float4(acc.v[0][j], acc.v[1][j], acc.v[2][j], acc.v[3][j]));
+    __stcg(reinterpret_cast<float4*>(row + 16), make_float4(acc.v[4][j], acc.v[5][j], acc.v[6][j], acc.v[7][j]));
+  }
+}
+// Reload `rows` feature rows from the compact scratch into a shared-memory tile (pitch LD).
+__device__ __forceinline__ void reload_rows(float* __restrict__ Y, const float* __restrict__ S, int rows) {
+  for (int idx = threadIdx.x; idx < rows * (BT / 4); idx += NT) {
+    const int r = idx / (BT / 4), c4 = idx % (BT / 4);
+    *reinterpret_cast<float4*>(Y + r * LD + c4 * 4) = __ldcg(reinterpret_cast<const float4*>(S + r * BT + c4 * 4));
+  }
+}
+
 // ---------------------------------------------------------------- the forward pass of one tile
 // smem tiles: XIN [(d+1)][LD] rows 0 = t, 1.. = x;  R1 [256][LD], R2 [128][LD], R3 [64][LD],
 // V [d][LD] receives nabla_V.  On return R1 holds o1 and R2 holds o2 (forward-only aliasing);
@@ -312,7 +331,8 @@ struct FwdMasks {
 template <bool kKeep>
 __device__ __forceinline__ void forward_tile(int d, const float* __restrict__ small, const SmallOff& so,
                                              const float* XIN, float* R1, float* R2, float* R3, float* O2,
-                                             float* O1, float* V, Pipe& pipe, const Coord& co, FwdMasks* masks) {
+                                             float* O1, float* V, Pipe& pipe, const Coord& co, FwdMasks* masks,
+                                             float* spill_r1 = nullptr, float* spill_r2 = nullptr) {
   // down_0: (d+1) -> 256, weights from L1/L2 (tiny K)
   {
     TileAcc<256> acc;
@@ -321,6 +341,7 @@ __device__ __forceinline__ void forward_tile(int d, const float* __restrict__ sm
     mac_chunk<256, 1, true>(acc, XIN, small + so.d0t, co, d + 1);
     relu_acc<256>(acc);
     store_tile<256>(acc, R1, co);
+    if (kKeep) spill_acc<256>(acc, spill_r1, co);
   }
   __syncthreads();
   // down_1: 256 -> 128
@@ -331,6 +352,7 @@ __device__ __forceinline__ void forward_tile(int d, const float* __restrict__ sm
     add_bias<128>(acc, small + so.b_d1, co);
     relu_acc<128>(acc);
     store_tile<128>(acc, R2, co);
+    if (kKeep) spill_acc<128>(acc, spill_r2, co);
   }
   __syncthreads();
   // down_2: 128 -> 64

@@ -106,6 +106,8 @@ def rollout(sde, x0: torch.Tensor, t: torch.Tensor, lmbd: float, *, noises: Opti
             ws.noises = noises
     if seed is None:
         seed = next_seed()
+    if B == 0:  # empty batch: nothing to launch (empty tensors have no device pointer)
+        return ws
     _lib.check(lib.socm_rollout_f32(
         desc.c_struct, udesc, wstruct, _lib.ptr(x0c), _lib.ptr(tab), noise_ptr, seed, path_offset, B, K,
         _lib.ptr(ws.states), _lib.ptr(ws.noises), _lib.ptr(ws.controls), _lib.ptr(ws.stop), _lib.ptr(ws.eff_dt),

@@ -62,7 +62,7 @@ def test_loss_and_grads_match_reference_golden(name):
 
 
 CASES = [  # kind, d, K, B, dense sigma
-    ("double_well", 10, 24, 70, False),
+    ("double_well", 10, 60, 70, False),
     ("ou_quadratic", 20, 12, 40, False),
     ("ou_linear", 10, 16, 33, True),
 ]
@@ -103,14 +103,14 @@ def test_chunked_equals_unchunked_and_scales_with_grad_output():
     hd, hm = [256, 128, 64], [128, 128]
     unet, mnet = seeded_unet(10, hd, 3), seeded_mnet(10, hm, 4)
     gam = {"gamma": torch.tensor([6.0]), "gamma2": torch.tensor([1.0]), "gamma3": torch.tensor([1.0])}
-    K, B = 12, 150
+    K, B = 60, 150
     noises = torch.randn(K, B, 10, generator=torch.Generator().manual_seed(8))
     res = []
     for chunk in (None, 64):
         sde = make_product_sde(st, unet, mnet, gam, hd, hm, DEV)
         res.append(run_product(sde, torch.zeros(10), K, B, 1.0, noises, "SOCM", chunk=chunk))
     (o1, g1), (o2, g2) = res
-    assert abs(float(o1[0]) - float(o2[0])) <= 1e-5 * abs(float(o1[0]))
+    assert torch.isfinite(o1[0]) and abs(float(o1[0]) - float(o2[0])) <= 1e-5 * abs(float(o1[0]))
     assert o1[7].shape == o2[7].shape == (K + 1, B)
     for k in g1:
         assert rel_l2(g2[k], g1[k]) <= 2e-5, (k, rel_l2(g2[k], g1[k]))

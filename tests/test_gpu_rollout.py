@@ -49,7 +49,7 @@ CASES = [  # kind, d, K, B, lmbd, dense sigma
     ("ou_quadratic", 5, 20, 64, 0.5, True),
     ("ou_linear", 10, 30, 65, 1.0, True),
     ("molecular_dynamics", 1, 150, 200, 1.0, False),
-    ("double_well", 32, 10, 3, 2.0, True),
+    ("double_well", 32, 150, 3, 2.0, True),
 ]
 
 
