@@ -76,7 +76,7 @@ class RolloutWorkspace:
 def rollout(sde, x0: torch.Tensor, t: torch.Tensor, lmbd: float, *, noises: Optional[torch.Tensor] = None,
             seed: Optional[int] = None, path_offset: int = 0, store_traj: bool = True,
             force_generic: bool = False, desc: Optional[SettingDesc] = None,
-            workspace: Optional[RolloutWorkspace] = None) -> RolloutWorkspace:
+            workspace: Optional[RolloutWorkspace] = None, timer=None) -> RolloutWorkspace:
     """Run K1 once.  Returns the workspace holding the outputs."""
     lib = _lib.load()
     _lib.require_cuda(x0, "x0")
@@ -108,11 +108,14 @@ def rollout(sde, x0: torch.Tensor, t: torch.Tensor, lmbd: float, *, noises: Opti
         seed = next_seed()
     if B == 0:  # empty batch: nothing to launch (empty tensors have no device pointer)
         return ws
-    _lib.check(lib.socm_rollout_f32(
-        desc.c_struct, udesc, wstruct, _lib.ptr(x0c), _lib.ptr(tab), noise_ptr, seed, path_offset, B, K,
-        _lib.ptr(ws.states), _lib.ptr(ws.noises), _lib.ptr(ws.controls), _lib.ptr(ws.stop), _lib.ptr(ws.eff_dt),
-        ws.lw[0].data_ptr(), ws.lw[1].data_ptr(), ws.lw[2].data_ptr(), _lib.ptr(ws.packed), flags,
-        _lib.stream_ptr()))
+    args = (desc.c_struct, udesc, wstruct, _lib.ptr(x0c), _lib.ptr(tab), noise_ptr, seed, path_offset, B, K,
+            _lib.ptr(ws.states), _lib.ptr(ws.noises), _lib.ptr(ws.controls), _lib.ptr(ws.stop), _lib.ptr(ws.eff_dt),
+            ws.lw[0].data_ptr(), ws.lw[1].data_ptr(), ws.lw[2].data_ptr(), _lib.ptr(ws.packed), flags,
+            _lib.stream_ptr())
+    if timer is not None:
+        timer("rollout", 2, lib.socm_rollout_f32, *args)
+    else:
+        _lib.check(lib.socm_rollout_f32(*args))
     del keep
     return ws
 

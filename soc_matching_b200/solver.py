@@ -63,6 +63,10 @@ class SOC_Solver(nn.Module):
         self.force_generic = False          # tests: run the shape-generic kernels
         self._injected_noise = None         # tests: (K, B, d) noise replayed by the next loss() call
         self._pair_grid = None
+        self.path_offset = 0                # first global path index of this rank (Philox counter)
+        self.kernel_events = None           # bench: dict name -> [(start, end) CUDA events] when not None
+        self.launch_count = 0               # kernels of libsocm_b200 launched by the last loss() call
+        self.last_stats = None              # fp64 [sum w, sum w^2, sum stop] of the last loss() call
 
     # ------------------------------------------------------------------ helpers
     def inject_noise(self, noises: Optional[torch.Tensor]):
@@ -82,6 +86,18 @@ class SOC_Solver(nn.Module):
         first = simulate.stochastic_trajectories(self.neural_sde, self.x0.repeat(batch_size, 1), self.ts,
                                                  self.lmbd)[0]
         return mean, err, first
+
+    def _timed(self, name, n_launches, fn, *args):
+        """Run one libsocm_b200 call; optionally bracket it with CUDA events on the current stream."""
+        self.launch_count += n_launches
+        if self.kernel_events is None:
+            return _lib.check(fn(*args))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(*args)
+        b.record()
+        self.kernel_events.setdefault(name, []).append((a, b))
+        return _lib.check(rc)
 
     def _grid(self):
         if self._pair_grid is None or self._pair_grid.t.device != self.ts.device:
@@ -154,6 +170,8 @@ class SOC_Solver(nn.Module):
             raise NotImplementedError("stopping-time SOCM is not chunked yet: batch_size must be <= chunk_paths")
 
         x0_rep = self.x0.detach().float().reshape(1, d)
+        ts_f32 = ts.float().contiguous()
+        self.launch_count = 0
         for start in range(0, B, chunk):
             nb = min(chunk, B - start)
             if nb != wsp.B:   # ragged last chunk
@@ -164,30 +182,31 @@ class SOC_Solver(nn.Module):
             if self._injected_noise is not None:
                 noises = self._injected_noise[:, start:start + nb].contiguous()
             simulate.rollout(sde, x0_rep.expand(nb, d).contiguous(), ts, self.lmbd, noises=noises, seed=seed,
-                             path_offset=start + getattr(self, "path_offset", 0), desc=desc, workspace=wsp,
-                             force_generic=self.force_generic)
-            _lib.check(lib.socm_target_prep_f32(
-                desc.c_struct, _lib.ptr(wsp.states), _lib.ptr(wsp.noises), _lib.ptr(wsp.controls),
-                _lib.ptr(wsp.eff_dt), wsp.lw[0].data_ptr(), wsp.lw[1].data_ptr(), wsp.lw[2].data_ptr(), nb, K,
-                _lib.ptr(R), ldr, _lib.ptr(wbuf), stream))
-            _lib.check(lib.socm_weight_stats_f32(_lib.ptr(wbuf), _lib.ptr(wsp.stop) if stopping else None, nb, K,
-                                                 _lib.ptr(stats), stream))
+                             path_offset=start + self.path_offset, desc=desc, workspace=wsp,
+                             force_generic=self.force_generic, timer=self._timed)
+            self._timed("prep", 1, lib.socm_target_prep_f32,
+                        desc.c_struct, _lib.ptr(wsp.states), _lib.ptr(wsp.noises), _lib.ptr(wsp.controls),
+                        _lib.ptr(wsp.eff_dt), wsp.lw[0].data_ptr(), wsp.lw[1].data_ptr(), wsp.lw[2].data_ptr(), nb, K,
+                        _lib.ptr(R), ldr, _lib.ptr(wbuf), stream)
+            self._timed("stats", 1, lib.socm_weight_stats_f32, _lib.ptr(wbuf),
+                        _lib.ptr(wsp.stop) if stopping else None, nb, K, _lib.ptr(stats), stream)
             if algorithm == "SOCM_const_M":
-                _lib.check(lib.socm_target_const_m_f32(_lib.ptr(R), nb, K, d, ldr, _lib.ptr(target), ldt, stream))
+                self._timed("target", 1, lib.socm_target_const_m_f32, _lib.ptr(R), nb, K, d, ldr, _lib.ptr(target),
+                            ldt, stream)
             elif not stopping:
-                _lib.check(lib.socm_target_gemm_f32(_lib.ptr(L.detach()), _lib.ptr(R), nb, K, d, ldr,
-                                                    _lib.ptr(target), ldt, stream))
+                self._timed("target", 1, lib.socm_target_gemm_f32, _lib.ptr(L.detach()), _lib.ptr(R), nb, K, d, ldr,
+                            _lib.ptr(target), ldt, stream)
             else:
                 target_graph = self._stopping_target(sde, wsp, R, ts, K, d, nb)
                 target[:, :nrows].copy_(target_graph.detach())
-            _lib.check(lib.socm_unet_loss_fwdbwd_f32(
-                desc.c_struct, udesc, warm_struct, _lib.ptr(ts.float().contiguous()), _lib.ptr(wsp.states),
-                _lib.ptr(target), ldt, _lib.ptr(wbuf), _lib.ptr(wsp.stop) if stopping else None, scale, nb, K,
-                _lib.ptr(G), _lib.ptr(grad_flat), _lib.ptr(loss_sum), _lib.ptr(loss_ws),
-                _lib.LOSS_FORCE_GENERIC if self.force_generic else 0, stream))
+            self._timed("loss_fwdbwd", 3, lib.socm_unet_loss_fwdbwd_f32,
+                        desc.c_struct, udesc, warm_struct, _lib.ptr(ts_f32), _lib.ptr(wsp.states),
+                        _lib.ptr(target), ldt, _lib.ptr(wbuf), _lib.ptr(wsp.stop) if stopping else None, scale, nb, K,
+                        _lib.ptr(G), _lib.ptr(grad_flat), _lib.ptr(loss_sum), _lib.ptr(loss_ws),
+                        _lib.LOSS_FORCE_GENERIC if self.force_generic else 0, stream)
             if L is not None:
-                _lib.check(lib.socm_target_gemm_bwd_f32(_lib.ptr(G), _lib.ptr(R), nb, K, d, ldr, ldt,
-                                                        _lib.ptr(dL), 1, stream))
+                self._timed("target_bwd", 1, lib.socm_target_gemm_bwd_f32, _lib.ptr(G), _lib.ptr(R), nb, K, d, ldr,
+                            ldt, _lib.ptr(dL), 1, stream)
             stop_all.append(wsp.stop if B <= chunk else wsp.stop.clone())
         self._injected_noise = None
         del keep
@@ -201,6 +220,7 @@ class SOC_Solver(nn.Module):
             lead, lead_grad = target_graph, (G[:, :nrows].double() / z).float()
         objective = _FusedObjective.apply(value.float(), lead, lead_grad, grad_flat, *uparams)
 
+        self.last_stats = stats
         mean_w = (stats[0] / B).float()
         var_w = (stats[1] - stats[0] * stats[0] / B) / max(B - 1, 1)       # unbiased, method.py:904
         std_w = torch.sqrt(torch.clamp(var_w, min=0.0)).float()
