@@ -58,13 +58,63 @@ __host__ __device__ inline GradOff grad_offsets(int d) {
   return g;
 }
 
-// per-CTA pitch of the private gradient buffers (keeps every buffer 128-byte aligned)
-__host__ __device__ inline int grad_stride(int d) { return ((grad_offsets(d).total + 31) / 32) * 32; }
-
 // ---------------------------------------------------------------- wgrad micro kernel
 // gw[n][c] += sum_p D[n][p] * A[c][p]   (D: N rows, A: C rows of the shared tiles, p = 64 points)
 // warp tile 32 n x 64 c (lanes 4 x 8, 8 x 8 outputs per thread, rows interleaved so that the float4
 // reads along p are bank-conflict free); warps tile [32*WN] x [64*WC].
+constexpr int PASS_FLOATS = NT * 64;  // one wgrad pass = 64 accumulators per thread
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Where element (n, c) of an N x C weight gradient lives inside its thread-major private block
+// (inverse of the mapping used by wgrad_tile); shared with reduce_grad_kernel.
+template <int N, int C>
+__host__ __device__ inline int wgrad_priv_index(int n, int c) {
+  constexpr int WC = C / 64, WN = 8 / WC;
+  const int pass = n / (32 * WN), nr = n % (32 * WN);
+  const int wn = nr / 32, ln = nr % 4, i = (nr % 32) / 4;
+  const int wc = c / 64, lc = c % 8, j = (c % 64) / 8;
+  const int t = (wn * WC + wc) * 32 + ln * 8 + lc;
+  const int k4 = 2 * i + j / 4;
+  return pass * PASS_FLOATS + (k4 * NT + t) * 4 + (j % 4);
+}
+template <int N, int C>
+__host__ __device__ constexpr int wgrad_priv_floats() {
+  return ((N + 32 * (8 / (C / 64)) - 1) / (32 * (8 / (C / 64)))) * PASS_FLOATS;
+}
+
+// CTA-private accumulation buffer: [flat part in GradOff layout (small layers, biases; the slots
+// of the six big weight matrices are unused)] [six thread-major wgrad blocks].
+struct PrivOff {
+  int d1, d2, r1, r2, u2, u1, total;
+};
+__host__ __device__ inline PrivOff priv_offsets(int d) {
+  PrivOff o;
+  int p = ((grad_offsets(d).total + 31) / 32) * 32;
+  o.d1 = p; p += wgrad_priv_floats<H1, H0>();
+  o.d2 = p; p += wgrad_priv_floats<H2, H1>();
+  o.r1 = p; p += wgrad_priv_floats<H0, H0>();
+  o.r2 = p; p += wgrad_priv_floats<H1, H1>();
+  o.u2 = p; p += wgrad_priv_floats<H1, H2>();
+  o.u1 = p; p += wgrad_priv_floats<H0, H1>();
+  o.total = p;
+  return o;
+}
+// per-CTA pitch of the private buffers
+__host__ __device__ inline int grad_stride(int d) { return priv_offsets(d).total; }
+// private offset of flat gradient element i
+__device__ __forceinline__ int priv_slot(const GradOff& go, const PrivOff& po, int i) {
+  if (i >= go.w[1] && i < go.b[1]) { const int e = i - go.w[1]; return po.d1 + wgrad_priv_index<H1, H0>(e / H0, e % H0); }
+  if (i >= go.w[2] && i < go.b[2]) { const int e = i - go.w[2]; return po.d2 + wgrad_priv_index<H2, H1>(e / H1, e % H1); }
+  if (i >= go.w[4] && i < go.b[4]) { const int e = i - go.w[4]; return po.r1 + wgrad_priv_index<H0, H0>(e / H0, e % H0); }
+  if (i >= go.w[5] && i < go.b[5]) { const int e = i - go.w[5]; return po.r2 + wgrad_priv_index<H1, H1>(e / H1, e % H1); }
+  if (i >= go.w[6] && i < go.b[6]) { const int e = i - go.w[6]; return po.u2 + wgrad_priv_index<H1, H2>(e / H2, e % H2); }
+  if (i >= go.w[7] && i < go.b[7]) { const int e = i - go.w[7]; return po.u1 + wgrad_priv_index<H0, H1>(e / H1, e % H1); }
+  return i;
+}
+
 template <int N, int C>
 __device__ __forceinline__ void wgrad_tile(const float* __restrict__ D, const float* __restrict__ A,
                                            float* __restrict__ gw) {
@@ -99,13 +149,16 @@ __device__ __forceinline__ void wgrad_tile(const float* __restrict__ D, const fl
         }
       }
     }
+    // accumulate into the CTA-private buffer: thread-major layout (float4 k4 of thread t at
+    // (k4 * 256 + t) * 4), so every warp-wide REDG.F32x4 is one contiguous 512-byte request and
+    // nothing is loaded back (fire-and-forget reduction at L2, no scoreboard stall)
+    float* base = gw + (size_t)((nb - wn * 32) / (32 * WN)) * PASS_FLOATS + threadIdx.x * 4;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float* g = gw + (size_t)(n0 + 4 * i) * C + (c0 + 8 * j);
-        __stcg(g, __ldcg(g) + acc[i][j]);
-      }
+      for (int h = 0; h < 2; ++h)
+        red_add_v4(base + (2 * i + h) * (NT * 4), acc[i][4 * h], acc[i][4 * h + 1], acc[i][4 * h + 2],
+                   acc[i][4 * h + 3]);
   }
 }
 
@@ -149,6 +202,7 @@ __global__ void __launch_bounds__(NT, 1) loss_tile_kernel(LossArgs a, const floa
   const int d = a.st.d, K = a.K, B = a.B;
   const SmallOff so = small_offsets(d);
   const GradOff go = grad_offsets(d);
+  const PrivOff po = priv_offsets(d);
   const float* small = packed + FT_FLOATS + BT_FLOATS;
   float* priv = priv_all + (size_t)blockIdx.x * grad_stride(d);
   float* scr = scratch_all + (size_t)blockIdx.x * SCR_FLOATS;
@@ -157,7 +211,7 @@ __global__ void __launch_bounds__(NT, 1) loss_tile_kernel(LossArgs a, const floa
   const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int tid = threadIdx.x;
 
-  for (int i = tid; i < go.total; i += NT) __stcg(priv + i, 0.f);  // private gradient accumulator
+  for (int i = tid; i < po.total; i += NT) __stcg(priv + i, 0.f);  // private gradient accumulator
   Pipe pipe;  // forward tape followed by backward tape = one contiguous 80-chunk tape
   pipe.start(smem + LS_STAGE, reinterpret_cast<uint64_t*>(smem + LS_BAR), packed, FT_CHUNKS + BT_CHUNKS,
              (uint32_t)my_tiles * (uint32_t)(FT_CHUNKS + BT_CHUNKS));
@@ -247,7 +301,7 @@ __global__ void __launch_bounds__(NT, 1) loss_tile_kernel(LossArgs a, const floa
     }
     __syncthreads();
     // ---- b2: up_1 wgrad: gW[256][128] += d_y1 (PA) x o2 (PB[0:128])
-    wgrad_tile<256, 128>(PA, PB, priv + go.w[7]);
+    wgrad_tile<256, 128>(PA, PB, priv + po.u1);
     bias_grad<256>(PA, priv + go.b[7]);
     // ---- b3: d_o2 = up_1^T d_y1 -> PB[0:128]; d_y2 = mask_y2 . d_o2 -> PA[0:128]
     {
@@ -260,7 +314,7 @@ __global__ void __launch_bounds__(NT, 1) loss_tile_kernel(LossArgs a, const floa
     }
     __syncthreads();
     // ---- b4: up_2 wgrad: gW[128][64] += d_y2 (PA[0:128]) x r3 (PB[128:192]); res_2 bias
-    wgrad_tile<128, 64>(PA, PB + H1 * LD, priv + go.w[6]);
+    wgrad_tile<128, 64>(PA, PB + H1 * LD, priv + po.u2);
     bias_grad<128>(PA, priv + go.b[6]);
     bias_grad<128>(PB, priv + go.b[5]);
     // ---- b5: d_z3 = relu'(r3) . (up_2^T d_y2) -> PB[192:256]
@@ -274,8 +328,8 @@ __global__ void __launch_bounds__(NT, 1) loss_tile_kernel(LossArgs a, const floa
     // ---- b6: r2 -> PA[128:256]; res_2 / down_2 wgrads
     reload_rows(PA + H1 * LD, scr + SCR_R2, H1);
     __syncthreads();
-    wgrad_tile<128, 128>(PB, PA + H1 * LD, priv + go.w[5]);
-    wgrad_tile<64, 128>(PB + (H1 + H2) * LD, PA + H1 * LD, priv + go.w[2]);
+    wgrad_tile<128, 128>(PB, PA + H1 * LD, priv + po.r2);
+    wgrad_tile<64, 128>(PB + (H1 + H2) * LD, PA + H1 * LD, priv + po.d2);
     bias_grad<64>(PB + (H1 + H2) * LD, priv + go.b[2]);
     // ---- b7: d_z2 = relu'(r2) . (res_2^T d_o2 + down_2^T d_z3) -> PA[0:128]
     {
@@ -289,7 +343,7 @@ __global__ void __launch_bounds__(NT, 1) loss_tile_kernel(LossArgs a, const floa
     // ---- b8: r1 -> PB; down_1 wgrad
     reload_rows(PB, scr + SCR_R1, H0);
     __syncthreads();
-    wgrad_tile<128, 256>(PA, PB, priv + go.w[1]);
+    wgrad_tile<128, 256>(PA, PB, priv + po.d1);
     bias_grad<128>(PA, priv + go.b[1]);
     // ---- b9..b12: d_z1 = relu'(r1) . (down_1^T d_z2 + res_1^T d_o1)
     {
@@ -303,7 +357,7 @@ __global__ void __launch_bounds__(NT, 1) loss_tile_kernel(LossArgs a, const floa
         store_tile<256>(o, PA, co);
       }
       __syncthreads();
-      wgrad_tile<256, 256>(PA, PB, priv + go.w[4]);
+      wgrad_tile<256, 256>(PA, PB, priv + po.r1);
       bias_grad<256>(PA, priv + go.b[4]);
       stream_layer<256, H0>(t, PA, pipe, co);  // + res_1^T d_o1
       mask_by_activation<256>(t, PB, co);
@@ -349,12 +403,15 @@ __global__ void __launch_bounds__(NT, 1) loss_tile_kernel(LossArgs a, const floa
   }
 }
 
-// grad[i] += sum over CTAs of priv[cta][i]   (fixed order: deterministic)
-__global__ void __launch_bounds__(256) reduce_grad_kernel(const float* __restrict__ priv_all, int n_cta, int n,
-                                                          int stride, float* __restrict__ grad) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+// grad[i] += sum over CTAs of their private slot of element i   (fixed order: deterministic)
+__global__ void __launch_bounds__(256) reduce_grad_kernel(const float* __restrict__ priv_all, int n_cta, int d,
+                                                          float* __restrict__ grad) {
+  const GradOff go = grad_offsets(d);
+  const PrivOff po = priv_offsets(d);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < go.total; i += gridDim.x * blockDim.x) {
+    const int slot = priv_slot(go, po, i);
     float s = 0.f;
-    for (int c = 0; c < n_cta; ++c) s += __ldcg(priv_all + (size_t)c * stride + i);
+    for (int c = 0; c < n_cta; ++c) s += __ldcg(priv_all + (size_t)c * po.total + slot);
     grad[i] += s;
   }
 }
@@ -385,7 +442,7 @@ int launch_loss_tile(const LossArgs& a, const socm_unet* net, float* grad, void*
   loss_tile_kernel<<<grid, NT, LS_BYTES, stream>>>(a, packed, priv, scratch);
   SOCM_LAUNCH_CHECK();
   const int n = grad_offsets(d).total;
-  reduce_grad_kernel<<<(n + 255) / 256, 256, 0, stream>>>(priv, grid, n, grad_stride(d), grad);
+  reduce_grad_kernel<<<(n + 255) / 256, 256, 0, stream>>>(priv, grid, d, grad);
   SOCM_LAUNCH_CHECK();
   return SOCM_OK;
 }

@@ -27,6 +27,7 @@ class PairGrid:
     s: torch.Tensor        # (P,)
     block_index: torch.Tensor  # (K+1, 2K+1) int64 into cat([M_all, dM_all, zero]) rows
     P: int
+    inverse_index: torch.Tensor = None  # (2P+1,) position of every source row in the block grid
 
 
 def make_pair_grid(ts: torch.Tensor, T: float) -> PairGrid:
@@ -53,15 +54,38 @@ def make_pair_grid(ts: torch.Tensor, T: float) -> PairGrid:
         idx[i, 2 * jm] = rows[: jm.shape[0]]            # M_ij
         idx[i, 2 * jm + 1] = P + rows[: jm.shape[0]]    # dM_ij
         idx[i, 2 * K] = rows[-1]                        # M_iK
+    n_blocks = (K + 1) * (2 * K + 1)
+    inv = torch.full((2 * P + 1,), n_blocks, dtype=torch.int64)    # default: the appended zero slot
+    flat = idx.reshape(-1)
+    used = flat != zero_row
+    inv[flat[used]] = torch.arange(n_blocks)[used]
     dev = ts.device
-    return PairGrid(K, t_vec.to(dev), s_vec.to(dev), idx.to(dev), P)
+    return PairGrid(K, t_vec.to(dev), s_vec.to(dev), idx.to(dev), P, inv.to(dev))
+
+
+class _GatherBlocks(torch.autograd.Function):
+    """blocks = cat([M, dM, 0])[block_index]; every source row lands in at most one block, so the
+    backward is a gather through the inverse map (no sort-based index_put accumulation)."""
+
+    @staticmethod
+    def forward(ctx, src, block_index, inverse_index):
+        ctx.save_for_backward(inverse_index)
+        return src[block_index]
+
+    @staticmethod
+    def backward(ctx, gblocks):
+        (inverse_index,) = ctx.saved_tensors
+        flat = gblocks.reshape(-1, *gblocks.shape[2:])
+        flat = torch.cat([flat, flat.new_zeros(1, *flat.shape[1:])], dim=0)   # slot for unused rows
+        return flat[inverse_index], None, None
 
 
 def build_L(m_all: torch.Tensor, dm_all: torch.Tensor, grid: PairGrid, ldr: int) -> torch.Tensor:
     """(P,d,d) x2 -> L ((K+1)d, ldr) fp32, zero-padded to the row pitch of R."""
     K, d = grid.K, m_all.shape[-1]
     zero = torch.zeros(1, d, d, device=m_all.device, dtype=m_all.dtype)
-    blocks = torch.cat([m_all, dm_all, zero], dim=0)[grid.block_index]        # (K+1, 2K+1, d, d)
+    src = torch.cat([m_all, dm_all, zero], dim=0)
+    blocks = _GatherBlocks.apply(src, grid.block_index, grid.inverse_index)   # (K+1, 2K+1, d, d)
     L = blocks.permute(0, 2, 1, 3).reshape((K + 1) * d, (2 * K + 1) * d)
     if ldr > L.shape[1]:
         L = torch.nn.functional.pad(L, (0, ldr - L.shape[1]))
