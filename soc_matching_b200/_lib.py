@@ -62,6 +62,7 @@ PROTOTYPES = {
 
 ROLLOUT_FORCE_GENERIC = 1
 ROLLOUT_NO_TRAJ = 2
+ROLLOUT_FORCE_FFMA = 4
 LOSS_FORCE_GENERIC = 1
 
 _lib = None

@@ -6,4 +6,11 @@ namespace socm {
 // Repack the nn.Linear weights of the default-arch UNet into the forward / backward tapes and
 // the small block (unet_tile.cuh); `packed` has tile::packed_floats(d) floats.
 int pack_tape(const socm_unet* net, float* packed, cudaStream_t stream);
+struct RolloutArgs;
+namespace tc {
+// tcgen05 rollout (rollout_tc.cu): default hdims and d <= 23
+bool rollout_tc_supported(const socm_unet* net);
+int64_t rollout_tc_workspace_bytes(int d);
+int launch_rollout_tc(const RolloutArgs& a, const socm_unet* net, void* workspace, cudaStream_t stream);
+}  // namespace tc
 }  // namespace socm

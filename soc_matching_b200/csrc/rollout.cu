@@ -8,6 +8,7 @@
 //                         fused into every step.  Default hdims only.
 //  rollout_generic_kernel one warp per path, any hdims.
 #include "kernels.h"
+#include "rollout_common.cuh"
 #include "unet_generic.cuh"
 #include "unet_tile.cuh"
 
@@ -62,69 +63,6 @@ int pack_tape(const socm_unet* net, float* packed, cudaStream_t stream) {
   pack_tape_kernel<<<64, 256, 0, stream>>>(*net, packed);
   SOCM_LAUNCH_CHECK();
   return SOCM_OK;
-}
-
-// ---------------------------------------------------------------- shared argument block
-struct RolloutArgs {
-  socm_setting st;
-  const float* warmA;
-  const float* warmc;
-  const float* x0;
-  const float* step_tab;
-  const float* noise_in;
-  uint64_t seed, path_offset;
-  int B, K;
-  float *states, *noises, *controls, *stop, *eff_dt, *lw_det, *lw_sto, *lw_term;
-};
-
-// eps[0..d) for (path m, step k): injected or Philox
-__device__ __forceinline__ void draw_noise(const RolloutArgs& a, int m, int k, float* eps) {
-  const int d = a.st.d;
-  if (a.noise_in != nullptr) {
-    const float* src = a.noise_in + ((size_t)k * a.B + m) * d;
-    for (int j = 0; j < d; ++j) eps[j] = __ldg(src + j);
-  } else {
-    for (int blk = 0; blk * 4 < d; ++blk) {
-      float z[4];
-      philox_normal4(a.seed, a.path_offset + (uint64_t)m, (uint32_t)k, (uint32_t)blk, z);
-      for (int j = 0; j < 4 && blk * 4 + j < d; ++j) eps[blk * 4 + j] = z[j];
-    }
-  }
-}
-
-// One path, one step, executed by ONE thread: draws noise, advances x, writes the outputs.
-__device__ __forceinline__ void path_step(const RolloutArgs& a, int m, int k, float* x, int ldx,
-                                          const float* gv, int ldv, PathAcc& acc) {
-  const int d = a.st.d, K = a.K;
-  float eps[kMaxDim], u[kMaxDim];
-  draw_noise(a, m, k, eps);
-  const float dt = __ldg(a.step_tab + k), sq_ldt = __ldg(a.step_tab + K + k);
-  const float dt_l = __ldg(a.step_tab + 2 * K + k), sq_dtl = __ldg(a.step_tab + 3 * K + k);
-  const float* wA = a.warmA ? a.warmA + (size_t)k * d * d : nullptr;
-  const float* wc = a.warmc ? a.warmc + (size_t)k * d : nullptr;
-  const float eff = sde_step(a.st, wA, wc, x, ldx, gv, ldv, eps, u, dt, sq_ldt, dt_l, sq_dtl, acc);
-  const size_t row = (size_t)k * a.B + m;
-  if (a.states) {
-    float* s = a.states + (row + a.B) * d;
-    for (int j = 0; j < d; ++j) s[j] = x[j * ldx];
-  }
-  if (a.controls) {
-    float* c = a.controls + row * d;
-    for (int j = 0; j < d; ++j) c[j] = u[j];
-  }
-  if (a.noises && a.noise_in == nullptr) {
-    float* n = a.noises + row * d;
-    for (int j = 0; j < d; ++j) n[j] = eps[j];
-  }
-  if (a.stop) a.stop[row + a.B] = acc.alive;
-  if (a.eff_dt) a.eff_dt[row] = eff;
-}
-
-__device__ __forceinline__ void path_finish(const RolloutArgs& a, int m, const float* x, int ldx,
-                                            const PathAcc& acc) {
-  a.lw_det[m] = acc.lw_det;
-  a.lw_sto[m] = acc.lw_sto;
-  a.lw_term[m] = __fdiv_rn(-term_cost(a.st, x, ldx), a.st.lmbd);  // utils.py:101
 }
 
 // ---------------------------------------------------------------- generic kernel (warp per path)
@@ -236,7 +174,9 @@ using namespace socm;
 
 extern "C" int64_t socm_rollout_workspace_bytes(const socm_unet* net) {
   if (!net) return -1;
-  return tile::packed_floats(net->d) * (int64_t)sizeof(float);
+  const int64_t ffma = tile::packed_floats(net->d) * (int64_t)sizeof(float);
+  const int64_t tcb = tc::rollout_tc_supported(net) ? tc::rollout_tc_workspace_bytes(net->d) : 0;
+  return ffma > tcb ? ffma : tcb;
 }
 
 extern "C" int socm_rollout_f32(const socm_setting* st, const socm_unet* net, const socm_warm_table* warm,
@@ -274,7 +214,10 @@ extern "C" int socm_rollout_f32(const socm_setting* st, const socm_unet* net, co
   a.lw_sto = logw_sto;
   a.lw_term = logw_term;
 
-  if (is_default_arch(net) && !(flags & SOCM_ROLLOUT_FORCE_GENERIC)) {
+  if (tc::rollout_tc_supported(net) && !(flags & (SOCM_ROLLOUT_FORCE_GENERIC | SOCM_ROLLOUT_FORCE_FFMA))) {
+    SOCM_CHECK_ARG(workspace != nullptr, "workspace is NULL (socm_rollout_workspace_bytes)");
+    if (int rc = tc::launch_rollout_tc(a, net, workspace, stream)) return rc;
+  } else if (is_default_arch(net) && !(flags & SOCM_ROLLOUT_FORCE_GENERIC)) {
     SOCM_CHECK_ARG(workspace != nullptr, "workspace is NULL (socm_rollout_workspace_bytes)");
     float* packed = static_cast<float*>(workspace);
     if (int rc = pack_tape(net, packed, stream)) return rc;

@@ -1,0 +1,211 @@
+// unet_tc.cuh -- tcgen05 (5th-gen tensor core) engine for the default FullyConnectedUNet
+// (hdims [256,128,64], models.py:202-242) at fp32-class accuracy ("3xTF32").
+//
+// Geometry.  One CTA owns a tile of TP = 128 trajectory points = the 128 lanes of tensor memory:
+// every GEMM is  D[128 points x N out-features] (+)= A[128 x K] * W^T[K x N]  with M = 128.
+//   * the accumulators D live in TMEM (fp32, one column per output feature);
+//   * the activations (A operand) are written back to TMEM by the epilogue threads
+//     (thread e <-> point e <-> TMEM lane e: no cross-thread traffic) and read by the next layer
+//     straight from TMEM (tcgen05.mma with A in tensor memory);
+//   * the two 256-wide activations (r1 = relu(down_0 x) and its re-use by res_1) do not fit next
+//     to the accumulators, so they are produced in 32-feature chunks into a double-buffered
+//     shared-memory A operand and consumed chunk by chunk;
+//   * the weights (B operand, K-major = nn.Linear's own [out][in] layout) are streamed from L2
+//     every step as a fixed tape of 32 KB slots by cp.async.bulk into a 3-stage ring
+//     (1.3 MB per 128 points and step; measured 132 GB/s per SM, see scripts/umma_probe.cu).
+//
+// Precision.  kind::tf32 truncates its fp32 inputs to 10 mantissa bits, so every product is
+// issued three times on split operands  x = hi + lo,  hi = rn_tf32(x), lo = x - hi (exact):
+//     a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo          (dropped a_lo*w_lo ~ 2^-24 |a w|)
+// with fp32 accumulation in TMEM.  Weights are split once per call by pack_tc_kernel, the
+// activations by the epilogue threads.
+//
+// TMEM column map (512 columns), forward pass:
+//   [0,256)    D0 = down_0 pre-activation (chunk source)  ->  r2 hi|lo  ->  o2 hi|lo  ->  D0 again
+//   [256,384)  D1 = down_1 acc  -> D2 = down_2 acc [256,320) -> D3 = up_2/res_2 acc
+//   [384,512)  r3 hi|lo
+//   [256,512)  D4 = up_1/res_1 acc (after D3 and r3 are dead)
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace socm {
+namespace tc {
+
+constexpr int TP = 128;  // points per tile
+constexpr int H0 = 256, H1 = 128, H2 = 64;
+constexpr int SLOT_BYTES = 32768;  // one tape slot / ring stage: hi slab + lo slab of a weight block
+constexpr int NSTAGE = 3;
+constexpr int CHUNK_F = 32;                   // features per shared-memory activation chunk
+constexpr int CHUNK_HALF = TP * CHUNK_F * 4;  // bytes of the hi (or lo) part of a chunk
+constexpr int CHUNK_BYTES = 2 * CHUNK_HALF;
+constexpr int MAX_KIN = 24;                   // d + 1 rounded up to 8; the engine covers d <= 23
+
+__host__ __device__ inline int kin_of(int d) { return ((d + 1 + 7) / 8) * 8; }
+__host__ __device__ inline int w0_slots(int d) { return kin_of(d) > 16 ? 2 : 1; }
+
+// ---------------------------------------------------------------- forward weight tape
+// slot order: [down_0 x S] [down_1 x 8] [down_2 x 2] [up_2 x 2] [res_2 x 4] [up_1 x 8] [res_1 x 16]
+struct SlotDesc {
+  int layer;  // index into socm_unet::w
+  int n0, N;  // output-feature range of the block
+  int k0, Kc; // input-feature range of the block (Kc multiple of 8)
+  int ktot;   // row length of the nn.Linear weight
+};
+__host__ __device__ inline int fwd_slots(int d) { return 40 + w0_slots(d); }
+__host__ __device__ inline SlotDesc fwd_slot(int d, int s) {
+  const int S = w0_slots(d), kin = kin_of(d);
+  if (s < S) return SlotDesc{0, s * (H0 / S), H0 / S, 0, kin, d + 1};
+  s -= S;
+  if (s < 8) return SlotDesc{1, 0, H1, 32 * s, 32, H0};
+  s -= 8;
+  if (s < 2) return SlotDesc{2, 0, H2, 64 * s, 64, H1};
+  s -= 2;
+  if (s < 2) return SlotDesc{6, 0, H1, 32 * s, 32, H2};
+  s -= 2;
+  if (s < 4) return SlotDesc{5, 0, H1, 32 * s, 32, H1};
+  s -= 4;
+  if (s < 8) return SlotDesc{7, 0, H0, 16 * s, 16, H1};
+  s -= 8;
+  return SlotDesc{4, 0, H0, 16 * s, 16, H0};
+}
+__host__ __device__ inline int slot_bytes(const SlotDesc& sd) { return 2 * sd.N * sd.Kc * 4; }
+
+// stage i of a forward pass (the consumption order repeats down_0 before res_1) -> tape slot
+__host__ __device__ inline int fwd_stages(int d) { return 40 + 2 * w0_slots(d); }
+__host__ __device__ inline int fwd_stage_slot(int d, int i) {
+  const int S = w0_slots(d);
+  if (i < S + 24) return i;
+  if (i < 2 * S + 24) return i - (S + 24);
+  return i - S;
+}
+
+// ---------------------------------------------------------------- small block (floats, fp32, read from shared memory)
+struct SmallTc {
+  int b_d0, b_d1, b_d2, b_u2, b_r2, b_u1, b_r1;
+  int u0t;   // up_0^T [256][dp]   (dp = d rounded up to 4)
+  int b_u0;  // [dp]
+  int r0;    // res_0 [d][kin]     (zero padded rows)
+  int b_r0;  // [dp]
+  int total;
+};
+__host__ __device__ inline SmallTc small_tc(int d) {
+  const int dp = ((d + 3) / 4) * 4, kin = kin_of(d);
+  SmallTc o;
+  int p = 0;
+  o.b_d0 = p; p += H0;
+  o.b_d1 = p; p += H1;
+  o.b_d2 = p; p += H2;
+  o.b_u2 = p; p += H1;
+  o.b_r2 = p; p += H1;
+  o.b_u1 = p; p += H0;
+  o.b_r1 = p; p += H0;
+  o.u0t = p; p += H0 * dp;
+  o.b_u0 = p; p += dp;
+  o.r0 = p; p += d * kin;
+  o.b_r0 = p; p += dp;
+  o.total = ((p + 3) / 4) * 4;
+  return o;
+}
+// workspace: [tape: fwd_slots x SLOT_BYTES][small block]
+__host__ __device__ inline int64_t tc_workspace_bytes(int d) {
+  return (int64_t)fwd_slots(d) * SLOT_BYTES + (int64_t)small_tc(d).total * 4;
+}
+
+// canonical no-swizzle K-major offsets (bytes)
+// weight slab [N rows][Kc cols]: core matrices contiguous along k, then along n
+__host__ __device__ inline int wslab_off(int n, int k, int Kc) {
+  return (n % 8) * 16 + (k % 4) * 4 + (n / 8) * (Kc * 32) + (k / 4) * 128;
+}
+// activation operand [128 points][F cols]: core matrices contiguous along the points, then along f
+__host__ __device__ inline int act_off(int p, int f) { return (p % 8) * 16 + (f % 4) * 4 + (p / 8) * 128 + (f / 4) * 2048; }
+constexpr uint32_t ACT_LBO = 2048, ACT_SBO = 128, ACT_KSTEP = 4096;  // descriptor strides of act_off
+constexpr uint32_t W_LBO = 128, W_KSTEP = 256;                       // weight slab: SBO = Kc * 32
+
+// ---------------------------------------------------------------- MMA issue helpers (elected thread)
+// one weight block against an A operand in TMEM (hi columns a_hi.., lo columns a_lo..)
+template <int N, int Kc>
+__device__ __forceinline__ void issue_block_ts(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_smem,
+                                               bool fresh) {
+  constexpr uint32_t id = umma::idesc_tf32(TP, N, 0, 0);
+  constexpr uint32_t slab = (uint32_t)N * Kc * 4;
+#pragma unroll
+  for (int ks = 0; ks < Kc / 8; ++ks) {
+    const uint64_t bh = umma::smem_desc(b_smem + ks * W_KSTEP, W_LBO, Kc * 32);
+    const uint64_t bl = umma::smem_desc(b_smem + slab + ks * W_KSTEP, W_LBO, Kc * 32);
+    umma::mma_ts(d_tmem, a_hi + ks * 8, bh, id, (fresh && ks == 0) ? 0u : 1u);
+    umma::mma_ts(d_tmem, a_lo + ks * 8, bh, id, 1u);
+    umma::mma_ts(d_tmem, a_hi + ks * 8, bl, id, 1u);
+  }
+}
+// one weight block against an A operand in shared memory (act_off layout; lo part at a_smem + a_lo_off)
+template <int N, int Kc>
+__device__ __forceinline__ void issue_block_ss(uint32_t d_tmem, uint32_t a_smem, uint32_t a_lo_off, uint32_t b_smem,
+                                               bool fresh) {
+  constexpr uint32_t id = umma::idesc_tf32(TP, N, 0, 0);
+  constexpr uint32_t slab = (uint32_t)N * Kc * 4;
+#pragma unroll
+  for (int ks = 0; ks < Kc / 8; ++ks) {
+    const uint64_t bh = umma::smem_desc(b_smem + ks * W_KSTEP, W_LBO, Kc * 32);
+    const uint64_t bl = umma::smem_desc(b_smem + slab + ks * W_KSTEP, W_LBO, Kc * 32);
+    const uint64_t ah = umma::smem_desc(a_smem + ks * ACT_KSTEP, ACT_LBO, ACT_SBO);
+    const uint64_t al = umma::smem_desc(a_smem + a_lo_off + ks * ACT_KSTEP, ACT_LBO, ACT_SBO);
+    umma::mma_ss(d_tmem, ah, bh, id, (fresh && ks == 0) ? 0u : 1u);
+    umma::mma_ss(d_tmem, al, bh, id, 1u);
+    umma::mma_ss(d_tmem, ah, bl, id, 1u);
+  }
+}
+
+// ---------------------------------------------------------------- epilogue helpers (thread <-> TMEM lane)
+// v[j] = max(v[j] + bias[j], 0) on 32 columns; bias in shared memory (broadcast reads)
+__device__ __forceinline__ void bias_relu32(float* v, const float* __restrict__ bias) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + j);
+    v[j] = fmaxf(v[j] + b.x, 0.f);
+    v[j + 1] = fmaxf(v[j + 1] + b.y, 0.f);
+    v[j + 2] = fmaxf(v[j + 2] + b.z, 0.f);
+    v[j + 3] = fmaxf(v[j + 3] + b.w, 0.f);
+  }
+}
+__device__ __forceinline__ void bias32(float* v, const float* __restrict__ bias) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + j);
+    v[j] += b.x;
+    v[j + 1] += b.y;
+    v[j + 2] += b.z;
+    v[j + 3] += b.w;
+  }
+}
+// TMEM A operand: hi -> columns a_hi.., lo -> columns a_lo..   (32 columns)
+__device__ __forceinline__ void store_split32(uint32_t a_hi, uint32_t a_lo, const float* v) {
+  uint32_t h[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) h[j] = __float_as_uint(umma::tf32_rn(v[j]));
+  umma::tmem_st32(a_hi, h);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) h[j] = __float_as_uint(v[j] - __uint_as_float(h[j]));
+  umma::tmem_st32(a_lo, h);
+}
+// shared-memory A operand chunk (32 features of point p): hi at chunk, lo at chunk + CHUNK_HALF
+__device__ __forceinline__ void store_chunk32(unsigned char* chunk, int p, const float* v) {
+  unsigned char* base = chunk + (p % 8) * 16 + (p / 8) * 128;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    float4 h, l;
+    h.x = umma::tf32_rn(v[4 * g]);
+    h.y = umma::tf32_rn(v[4 * g + 1]);
+    h.z = umma::tf32_rn(v[4 * g + 2]);
+    h.w = umma::tf32_rn(v[4 * g + 3]);
+    l.x = v[4 * g] - h.x;
+    l.y = v[4 * g + 1] - h.y;
+    l.z = v[4 * g + 2] - h.z;
+    l.w = v[4 * g + 3] - h.w;
+    *reinterpret_cast<float4*>(base + g * 2048) = h;
+    *reinterpret_cast<float4*>(base + CHUNK_HALF + g * 2048) = l;
+  }
+}
+
+}  // namespace tc
+}  // namespace socm

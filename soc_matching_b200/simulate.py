@@ -75,9 +75,11 @@ class RolloutWorkspace:
 
 def rollout(sde, x0: torch.Tensor, t: torch.Tensor, lmbd: float, *, noises: Optional[torch.Tensor] = None,
             seed: Optional[int] = None, path_offset: int = 0, store_traj: bool = True,
-            force_generic: bool = False, desc: Optional[SettingDesc] = None,
+            force_generic: bool = False, force_ffma: bool = False, desc: Optional[SettingDesc] = None,
             workspace: Optional[RolloutWorkspace] = None, timer=None) -> RolloutWorkspace:
-    """Run K1 once.  Returns the workspace holding the outputs."""
+    """Run K1 once.  Returns the workspace holding the outputs.  Kernel selection (csrc/rollout.cu):
+    default hdims -> tcgen05 tensor-core kernel (3xTF32); ``force_ffma`` -> fp32 FFMA tile kernel;
+    ``force_generic`` / other hdims -> shape-generic warp-per-path kernel."""
     lib = _lib.load()
     _lib.require_cuda(x0, "x0")
     if not getattr(sde, "use_learned_control", False):
@@ -95,7 +97,8 @@ def rollout(sde, x0: torch.Tensor, t: torch.Tensor, lmbd: float, *, noises: Opti
     x0c = x0.detach().float().contiguous()
     warm = resolve_warm_start(sde, t)
     wstruct = _warm_struct(warm.A_roll, warm.c_roll) if warm is not None else None
-    flags = (0 if store_traj else _lib.ROLLOUT_NO_TRAJ) | (_lib.ROLLOUT_FORCE_GENERIC if force_generic else 0)
+    flags = ((0 if store_traj else _lib.ROLLOUT_NO_TRAJ) | (_lib.ROLLOUT_FORCE_GENERIC if force_generic else 0)
+             | (_lib.ROLLOUT_FORCE_FFMA if force_ffma else 0))
     noise_ptr = None
     if noises is not None:
         _lib.require_cuda(noises, "noises")
@@ -121,7 +124,7 @@ def rollout(sde, x0: torch.Tensor, t: torch.Tensor, lmbd: float, *, noises: Opti
 
 
 def stochastic_trajectories(sde, x0, t, lmbd, detach=True, verbose=False, *, noises=None, seed=None,
-                            force_generic=False):
+                            force_generic=False, force_ffma=False):
     """Same signature and 8-tuple as utils.py:17-128:
     (states (K+1,B,d), noises (K,B,d), stop_indicators (K+1,B), fractional_timesteps (K,B),
      log_path_weight_deterministic (B,), log_path_weight_stochastic (B,), log_terminal_weight (B,),
@@ -132,7 +135,7 @@ def stochastic_trajectories(sde, x0, t, lmbd, detach=True, verbose=False, *, noi
     scope) is not supported: the fused kernel does not record an autograd graph."""
     if not detach:
         raise NotImplementedError("detach=False (back-propagation through the rollout) is not supported")
-    ws = rollout(sde, x0, t, lmbd, noises=noises, seed=seed, force_generic=force_generic)
+    ws = rollout(sde, x0, t, lmbd, noises=noises, seed=seed, force_generic=force_generic, force_ffma=force_ffma)
     return (ws.states, ws.noises, ws.stop, ws.eff_dt, ws.lw[0], ws.lw[1], ws.lw[2], ws.controls)
 
 

@@ -37,10 +37,10 @@ def test_rollout_matches_reference_golden(name):
     x0 = g.x0.to(DEV).repeat(g.meta["B"], 1)
     out = sb.stochastic_trajectories(sde, x0, g.ts.to(DEV), g.meta["lmbd"], noises=g.traj[1].to(DEV))
     compare_rollout(out, g.traj)
-    if g.meta["hdims"] == [256, 128, 64]:  # also the shape-generic kernel on the full-width net
-        out2 = sb.stochastic_trajectories(sde, x0, g.ts.to(DEV), g.meta["lmbd"], noises=g.traj[1].to(DEV),
-                                          force_generic=True)
-        compare_rollout(out2, g.traj)
+    if g.meta["hdims"] == [256, 128, 64]:  # also the FFMA tile and shape-generic kernels on the full-width net
+        for kw in ({"force_ffma": True}, {"force_generic": True}):
+            out2 = sb.stochastic_trajectories(sde, x0, g.ts.to(DEV), g.meta["lmbd"], noises=g.traj[1].to(DEV), **kw)
+            compare_rollout(out2, g.traj)
 
 
 CASES = [  # kind, d, K, B, lmbd, dense sigma
@@ -54,8 +54,8 @@ CASES = [  # kind, d, K, B, lmbd, dense sigma
 
 
 @pytest.mark.parametrize("kind,d,K,B,lmbd,dense", CASES)
-@pytest.mark.parametrize("generic", [False, True])
-def test_rollout_default_width_matches_oracle(kind, d, K, B, lmbd, dense, generic):
+@pytest.mark.parametrize("kernel", ["tc", "ffma", "generic"])
+def test_rollout_default_width_matches_oracle(kind, d, K, B, lmbd, dense, kernel):
     import soc_matching_b200 as sb
     st = random_setting(kind, d, seed=d * 7 + K, lmbd=lmbd, dense_sigma=dense)
     hd, hm = [256, 128, 64], [32, 32]
@@ -70,7 +70,7 @@ def test_rollout_default_width_matches_oracle(kind, d, K, B, lmbd, dense, generi
     want = orc.rollout(st, unet, x0.repeat(B, 1), ts, noises=noises)
     sde = make_product_sde(st, unet, mnet, gam, hd, hm, DEV, stopping=(kind == "molecular_dynamics"))
     got = sb.stochastic_trajectories(sde, x0.to(DEV).repeat(B, 1), ts.to(DEV), lmbd, noises=noises.to(DEV),
-                                     force_generic=generic)
+                                     force_generic=(kernel == "generic"), force_ffma=(kernel == "ffma"))
     if kind == "molecular_dynamics":
         assert (want[2][-1] == 0).sum() > 5, "test needs stopped paths"
     compare_rollout(got, want)
