@@ -312,4 +312,62 @@ __device__ __forceinline__ float sde_step(const socm_setting& st, const float* w
   return eff_dt;
 }
 
+// ---------------------------------------------------------------- register-resident variant of sde_step
+// for the "diagonal" settings: sigma = identity, double-well type drift (kinds DOUBLE_WELL and
+// MOLECULAR_DYNAMICS), no warm start.  Same operations in the same order as sde_step, but on DM
+// compile-time lanes (DM >= d; lanes >= d must hold zeros in x, gv, eps, kap and stay zero), so
+// every vector lives in registers.  kap[] = kappa padded with zeros.
+__host__ __device__ inline bool diag_fast_path(const socm_setting& st, bool warm) {
+  return st.sigma_is_identity && !warm && (st.kind == SOCM_DOUBLE_WELL || st.kind == SOCM_MOLECULAR_DYNAMICS);
+}
+
+template <int DM>
+__device__ __forceinline__ float sde_step_diag(bool md, float lmbd, const float* kap, float* x, const float* gv,
+                                               const float* eps, float* u, float dt, float sq_ldt, float dt_l,
+                                               float sq_dtl, PathAcc& acc) {
+  float tmp[DM];
+#pragma unroll
+  for (int i = 0; i < DM; ++i) {
+    u[i] = -gv[i];
+    tmp[i] = __fadd_rn(dw_drift(kap[i], x[i]), u[i]);
+    tmp[i] = __fadd_rn(__fmul_rn(tmp[i], dt), __fmul_rn(sq_ldt, eps[i]));
+  }
+  float eff_dt = dt;
+  float a_l = dt_l, sq_l = sq_dtl;
+  if (md) {
+    const float phi0 = -x[0];
+    const float xn0 = __fadd_rn(x[0], __fmul_rn(acc.alive, tmp[0]));
+    const float phi1 = -xn0;
+    const float still = (phi0 > 0.f && phi1 > 0.f) ? 1.f : 0.f;
+    const float crossed = (phi0 > 0.f && phi1 < 0.f) ? 1.f : 0.f;
+    const float frac =
+        __fmul_rn(crossed, __fadd_rn(__fdiv_rn(phi0, __fadd_rn(__fadd_rn(phi0, -phi1), 1e-6f)), 1e-6f));
+    const float fa = __fmul_rn(frac, acc.alive);
+#pragma unroll
+    for (int i = 0; i < DM; ++i) {
+      const float xb = x[i];
+      const float xn = __fadd_rn(xb, __fmul_rn(acc.alive, tmp[i]));
+      const float xf = __fadd_rn(xb, __fmul_rn(fa, tmp[i]));
+      x[i] = __fadd_rn(__fmul_rn(crossed, xf), __fmul_rn(__fadd_rn(1.f, -crossed), xn));
+    }
+    eff_dt = __fadd_rn(__fmul_rn(__fmul_rn(crossed, __fmul_rn(frac, frac)), dt), __fmul_rn(still, dt));
+    acc.alive = (-x[0] > 0.f) ? 1.f : 0.f;
+    a_l = __fdiv_rn(eff_dt, lmbd);
+    sq_l = __fsqrt_rn(a_l);
+  } else {
+#pragma unroll
+    for (int i = 0; i < DM; ++i) x[i] = __fadd_rn(x[i], __fmul_rn(acc.alive, tmp[i]));
+  }
+  float uu = 0.f, ue = 0.f;
+#pragma unroll
+  for (int i = 0; i < DM; ++i) {
+    uu = __fadd_rn(uu, __fmul_rn(u[i], u[i]));
+    ue = __fadd_rn(ue, __fmul_rn(u[i], eps[i]));
+  }
+  const float f = md ? 1.0f : 0.0f;
+  acc.lw_det = __fadd_rn(acc.lw_det, __fmul_rn(a_l, __fadd_rn(-f, -__fmul_rn(0.5f, uu))));
+  acc.lw_sto = __fadd_rn(acc.lw_sto, __fmul_rn(sq_l, -ue));
+  return eff_dt;
+}
+
 }  // namespace socm

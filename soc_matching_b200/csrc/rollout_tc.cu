@@ -12,6 +12,8 @@
 //   warp 5     "P": streams the weight tape from L2 into the 3-stage ring (cp.async.bulk).
 // Hand-offs are mbarriers; each of the per-step events below completes exactly once per step, so
 // its wait parity is the step parity.
+#include <type_traits>
+
 #include "kernels.h"
 #include "rollout_common.cuh"
 #include "unet_tc.cuh"
@@ -23,7 +25,7 @@ using namespace umma;
 
 // ---------------------------------------------------------------- weight repack (once per call)
 __global__ void pack_tc_kernel(socm_unet net, unsigned char* __restrict__ tape, float* __restrict__ small) {
-  const int d = net.d, kin = kin_of(d), dp = ((d + 3) / 4) * 4;
+  const int d = net.d, kin = kin_of(d);
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   const int n_slots = fwd_slots(d);
   for (int s = 0; s < n_slots; ++s) {
@@ -51,17 +53,17 @@ __global__ void pack_tc_kernel(socm_unet net, unsigned char* __restrict__ tape, 
   copy(so.b_r2, net.b[5], H1);
   copy(so.b_u1, net.b[7], H0);
   copy(so.b_r1, net.b[4], H0);
-  for (int i = tid; i < H0 * dp; i += nth) {
-    const int f = i / dp, j = i - f * dp;
+  for (int i = tid; i < H0 * kin; i += nth) {
+    const int f = i / kin, j = i - f * kin;
     small[so.u0t + i] = j < d ? net.w[8][(size_t)j * H0 + f] : 0.f;
   }
-  for (int i = tid; i < dp; i += nth) {
+  for (int i = tid; i < kin; i += nth) {
     small[so.b_u0 + i] = i < d ? net.b[8][i] : 0.f;
     small[so.b_r0 + i] = i < d ? net.b[3][i] : 0.f;
   }
-  for (int i = tid; i < d * kin; i += nth) {
+  for (int i = tid; i < kin * kin; i += nth) {
     const int j = i / kin, k = i - j * kin;
-    small[so.r0 + i] = k <= d ? net.w[3][(size_t)j * (d + 1) + k] : 0.f;
+    small[so.r0 + i] = (j < d && k <= d) ? net.w[3][(size_t)j * (d + 1) + k] : 0.f;
   }
 }
 
@@ -77,9 +79,51 @@ enum Bar {
 };
 __host__ __device__ inline int rollout_tc_smem_bytes(int d) { return SM_SMALL + small_tc(d).total * 4 + N_BARS * 8 + 16; }
 
-constexpr int NT_TC = 192;
+constexpr int NT_TC = 320;  // 8 epilogue warps + MMA warp + producer warp
+constexpr int NE = 256;     // epilogue threads
+
+#ifdef SOCM_TC_PROF
+// per-phase cycle accumulators of block 0 (E thread 0: slots 0-15, M warp: slots 16-31); debug builds only
+__device__ unsigned long long g_tc_prof[48];
+#define PROF_DECL long long prof_t = clock64(); unsigned long long prof_acc[16] = {0}
+#define PROF_MARK(i) do { const long long t_ = clock64(); prof_acc[i] += (unsigned long long)(t_ - prof_t); prof_t = t_; } while (0)
+#define PROF_FLUSH(base, cond) do { if (blockIdx.x == 0 && (cond)) for (int i_ = 0; i_ < 16; ++i_) g_tc_prof[(base) + i_] = prof_acc[i_]; } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(i)
+#define PROF_FLUSH(base, cond)
+#endif
 // TMEM columns
 constexpr uint32_t C_SA = 0, C_D1 = 256, C_D2 = 256, C_D3 = 256, C_R3 = 384, C_D4 = 256;
+
+// one arrival per warp (the barrier counts warps): every lane's writes are ordered before it by __syncwarp
+__device__ __forceinline__ void warp_arrive(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
+__device__ __forceinline__ void e_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the 8 E warps
+
+// eps[0..d) for (path m, step k) into registers: injected or Philox (same draws as draw_noise)
+template <int KIN>
+__device__ __forceinline__ void draw_noise_reg(const RolloutArgs& a, int m, int k, float* eps) {
+  const int d = a.st.d;
+  if (a.noise_in != nullptr) {
+    const float* src = a.noise_in + ((size_t)k * a.B + m) * d;
+#pragma unroll
+    for (int j = 0; j < KIN; ++j)
+      if (j < d) eps[j] = __ldg(src + j);
+  } else {
+#pragma unroll
+    for (int blk = 0; blk < KIN / 4; ++blk) {
+      if (blk * 4 < d) {
+        float z[4];
+        philox_normal4(a.seed, a.path_offset + (uint64_t)m, (uint32_t)k, (uint32_t)blk, z);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) eps[blk * 4 + j] = (blk * 4 + j < d) ? z[j] : 0.f;
+      }
+    }
+  }
+}
 
 template <int KIN>
 __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, const unsigned char* __restrict__ tape,
@@ -93,6 +137,7 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
   const int tid = threadIdx.x, warp = tid >> 5;
   const int n_tiles = (B + TP - 1) / TP;
   const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const bool diag = diag_fast_path(a.st, a.warmA != nullptr);
   constexpr int S0 = KIN > 16 ? 2 : 1;        // down_0 slots
   constexpr int NS = 40 + 2 * S0;             // weight stages per step
 
@@ -104,62 +149,78 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
       mbar_init(&bars[W_EMPTY + s], 1);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&bars[CH_FULL + b], TP);
+      mbar_init(&bars[CH_FULL + b], NE / 32);
       mbar_init(&bars[CH_EMPTY + b], 1);
     }
-    const int e2m[] = {XIN_FULL, R2_FULL, R3_FULL, Y2_FULL, O2_FULL, Y1_FULL};
-    for (int i = 0; i < 6; ++i) mbar_init(&bars[e2m[i]], TP);
+    mbar_init(&bars[XIN_FULL], TP / 32);
+    const int e2m[] = {R2_FULL, R3_FULL, Y2_FULL, O2_FULL, Y1_FULL};
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[e2m[i]], NE / 32);
     const int m2e[] = {D0_FULL, D1_FULL, D2_FULL, D3A_FULL, D3B_FULL, D4A_FULL, D0B_FULL, D4B_FULL};
     for (int i = 0; i < 8; ++i) mbar_init(&bars[m2e[i]], 1);
     mbar_init_fence();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, 512);
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tm = *tmem_slot;
   const uint32_t ring_s = smem_addr(smem + SM_RING), chunk_s = smem_addr(smem + SM_CHUNK), xin_s = smem_addr(smem + SM_XIN);
 
-  if (warp < 4) {
+  if (warp < 8) {
     // =================================================================== E: epilogue / path threads
-    const int e = tid;
-    const uint32_t lane_t = tm + ((uint32_t)(warp * 32) << 16);  // this warp's TMEM lane quarter
+    // thread -> TMEM lane p (= path of the tile) and column half h: the two warps that share a lane
+    // quarter split every accumulator's columns.  h == 0 threads own the path state.
+    // The two halves run separately compiled copies of the program (h is a compile-time constant)
+    // so that owner-only and helper-only values do not add up in the register allocation.
+    auto e_program = [&](auto h_const) {
+    constexpr int h = decltype(h_const)::value;
+    const int p = tid & (TP - 1);
+    const uint32_t lane_t = tm + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t g = 0;   // steps done (all tiles)
     uint32_t cu = 0;  // chunks produced
+    PROF_DECL;
     float* xin_hi = reinterpret_cast<float*>(smem + SM_XIN);
     float* xin_lo = reinterpret_cast<float*>(smem + SM_XIN + KIN * 512);
+    float* stage_f = reinterpret_cast<float*>(smem + SM_CHUNK);  // exchange area (chunk buffer 0, idle after res_1)
 
-    auto gen_chunks = [&]() {  // r1 = relu(D0 + b_d0) -> 8 shared-memory A chunks
+    float kap[KIN];  // kappa padded with zeros (diagonal fast path of the SDE step)
+#pragma unroll
+    for (int j = 0; j < KIN; ++j) kap[j] = (h == 0 && diag && j < d) ? __ldg(a.st.kappa + j) : 0.f;
+
+    auto gen_chunks = [&]() {  // r1 = relu(D0 + b_d0) -> 8 shared-memory A chunks, 16 features per half
       for (int c = 0; c < 8; ++c) {
         const int b = cu & 1;
         mbar_wait(&bars[CH_EMPTY + b], ((cu >> 1) & 1) ^ 1);
-        float v[32];
-        tmem_ld32(lane_t + C_SA + 32 * c, reinterpret_cast<uint32_t*>(v));
+        float v[16];
+        tmem_ld16(lane_t + C_SA + 32 * c + 16 * h, reinterpret_cast<uint32_t*>(v));
         tmem_wait_ld();
-        bias_relu32(v, sm_small + so.b_d0 + 32 * c);
-        store_chunk32(smem + SM_CHUNK + b * CHUNK_BYTES, e, v);
+        bias_relu16(v, sm_small + so.b_d0 + 32 * c + 16 * h);
+        store_chunk16(smem + SM_CHUNK + b * CHUNK_BYTES, p, 4 * h, v);
         fence_async_smem();
-        mbar_arrive(&bars[CH_FULL + b]);
+        warp_arrive(&bars[CH_FULL + b]);
         ++cu;
       }
     };
 
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      const int m = t * TP + e;
+      const int m = t * TP + p;
       const bool live = m < B;
-      float x[KIN];  // x[j], j < d
+      float x[KIN];  // owner threads: x[j], j < d
       PathAcc acc{1.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < KIN; ++j) x[j] = (j < d && live) ? __ldg(a.x0 + (size_t)m * d + j) : 0.f;
-      if (live) {
-        if (a.states)
-          for (int j = 0; j < d; ++j) a.states[(size_t)m * d + j] = x[j];
+      for (int j = 0; j < KIN; ++j) x[j] = (j < d && live && h == 0) ? __ldg(a.x0 + (size_t)m * d + j) : 0.f;
+      if (live && h == 0) {
+        if (a.states) {
+#pragma unroll
+          for (int j = 0; j < KIN; ++j)
+            if (j < d) a.states[(size_t)m * d + j] = x[j];
+        }
         if (a.stop) a.stop[m] = 1.f;
       }
       for (int k = 0; k < K; ++k, ++g) {
         const uint32_t ph = g & 1;
-        // ---- E0: input operand [t, x, 0..] (hi / lo), act_off layout
-        {
+        // ---- E0 (owners): input operand [t, x, 0..] (hi / lo), act_off layout
+        if (h == 0) {
           const float tk = __ldg(a.step_tab + 4 * K + k);
 #pragma unroll
           for (int c4 = 0; c4 < KIN / 4; ++c4) {
@@ -170,28 +231,29 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
               v[q] = c == 0 ? tk : x[c - 1 < 0 ? 0 : c - 1];
               if (c > d) v[q] = 0.f;
             }
-            float4 h, l;
-            h.x = tf32_rn(v[0]); h.y = tf32_rn(v[1]); h.z = tf32_rn(v[2]); h.w = tf32_rn(v[3]);
-            l.x = v[0] - h.x; l.y = v[1] - h.y; l.z = v[2] - h.z; l.w = v[3] - h.w;
-            const int off = (e % 8) * 4 + (e / 8) * 32 + c4 * 512;  // floats
-            *reinterpret_cast<float4*>(xin_hi + off) = h;
-            *reinterpret_cast<float4*>(xin_lo + off) = l;
+            float4 hh, ll;
+            hh.x = tf32_rn(v[0]); hh.y = tf32_rn(v[1]); hh.z = tf32_rn(v[2]); hh.w = tf32_rn(v[3]);
+            ll.x = v[0] - hh.x; ll.y = v[1] - hh.y; ll.z = v[2] - hh.z; ll.w = v[3] - hh.w;
+            const int off = (p % 8) * 4 + (p / 8) * 32 + c4 * 512;  // floats
+            *reinterpret_cast<float4*>(xin_hi + off) = hh;
+            *reinterpret_cast<float4*>(xin_lo + off) = ll;
           }
           fence_async_smem();
-          mbar_arrive(&bars[XIN_FULL]);
+          warp_arrive(&bars[XIN_FULL]);
         }
-        // noise of this step (overlaps the first MMAs)
-        float eps[kMaxDim];
-        if (live) draw_noise(a, m, k, eps);
+        PROF_MARK(0);
         // ---- E1: r1 chunks for down_1
         mbar_wait(&bars[D0_FULL], ph);
+        PROF_MARK(2);
         fence_after_sync();
         gen_chunks();
-        // ---- E2: r2 = relu(D1 + b) -> TMEM A operand [0,128) hi, [128,256) lo
+        PROF_MARK(3);
+        // ---- E2: r2 = relu(D1 + b) -> TMEM A operand [0,128) hi, [128,256) lo   (64 columns per half)
         mbar_wait(&bars[D1_FULL], ph);
+        PROF_MARK(4);
         fence_after_sync();
 #pragma unroll 1
-        for (int cb = 0; cb < 4; ++cb) {
+        for (int cb = 2 * h; cb < 2 * h + 2; ++cb) {
           float v[32];
           tmem_ld32(lane_t + C_D1 + 32 * cb, reinterpret_cast<uint32_t*>(v));
           tmem_wait_ld();
@@ -200,26 +262,29 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
         }
         tmem_wait_st();
         fence_before_sync();
-        mbar_arrive(&bars[R2_FULL]);
-        // ---- E3: r3 = relu(D2 + b) -> [384,448) hi, [448,512) lo
+        warp_arrive(&bars[R2_FULL]);
+        PROF_MARK(5);
+        // ---- E3: r3 = relu(D2 + b) -> [384,448) hi, [448,512) lo   (32 columns per half)
         mbar_wait(&bars[D2_FULL], ph);
+        PROF_MARK(6);
         fence_after_sync();
-#pragma unroll 1
-        for (int cb = 0; cb < 2; ++cb) {
+        {
           float v[32];
-          tmem_ld32(lane_t + C_D2 + 32 * cb, reinterpret_cast<uint32_t*>(v));
+          tmem_ld32(lane_t + C_D2 + 32 * h, reinterpret_cast<uint32_t*>(v));
           tmem_wait_ld();
-          bias_relu32(v, sm_small + so.b_d2 + 32 * cb);
-          store_split32(lane_t + C_R3 + 32 * cb, lane_t + C_R3 + 64 + 32 * cb, v);
+          bias_relu32(v, sm_small + so.b_d2 + 32 * h);
+          store_split32(lane_t + C_R3 + 32 * h, lane_t + C_R3 + 64 + 32 * h, v);
         }
         tmem_wait_st();
         fence_before_sync();
-        mbar_arrive(&bars[R3_FULL]);
+        warp_arrive(&bars[R3_FULL]);
+        PROF_MARK(5);
         // ---- E4: y2 = relu(D3 + b_u2) in place
         mbar_wait(&bars[D3A_FULL], ph);
+        PROF_MARK(6);
         fence_after_sync();
 #pragma unroll 1
-        for (int cb = 0; cb < 4; ++cb) {
+        for (int cb = 2 * h; cb < 2 * h + 2; ++cb) {
           float v[32];
           tmem_ld32(lane_t + C_D3 + 32 * cb, reinterpret_cast<uint32_t*>(v));
           tmem_wait_ld();
@@ -228,12 +293,14 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
         }
         tmem_wait_st();
         fence_before_sync();
-        mbar_arrive(&bars[Y2_FULL]);
+        warp_arrive(&bars[Y2_FULL]);
+        PROF_MARK(5);
         // ---- E5: o2 = D3 + b_r2 -> TMEM A operand [0,128) hi, [128,256) lo
         mbar_wait(&bars[D3B_FULL], ph);
+        PROF_MARK(7);
         fence_after_sync();
 #pragma unroll 1
-        for (int cb = 0; cb < 4; ++cb) {
+        for (int cb = 2 * h; cb < 2 * h + 2; ++cb) {
           float v[32];
           tmem_ld32(lane_t + C_D3 + 32 * cb, reinterpret_cast<uint32_t*>(v));
           tmem_wait_ld();
@@ -242,12 +309,20 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
         }
         tmem_wait_st();
         fence_before_sync();
-        mbar_arrive(&bars[O2_FULL]);
-        // ---- E6: y1 = relu(D4 + b_u1) in place
+        warp_arrive(&bars[O2_FULL]);
+        PROF_MARK(5);
+        // up_1 runs for ~6k cycles now: the helper half draws this step's noise meanwhile
+        float eps[KIN];
+#pragma unroll
+        for (int j = 0; j < KIN; ++j) eps[j] = 0.f;
+        if (h == 1 && live) draw_noise_reg<KIN>(a, m, k, eps);
+        PROF_MARK(1);
+        // ---- E6: y1 = relu(D4 + b_u1) in place   (128 columns per half)
         mbar_wait(&bars[D4A_FULL], ph);
+        PROF_MARK(8);
         fence_after_sync();
 #pragma unroll 1
-        for (int cb = 0; cb < 8; ++cb) {
+        for (int cb = 4 * h; cb < 4 * h + 4; ++cb) {
           float v[32];
           tmem_ld32(lane_t + C_D4 + 32 * cb, reinterpret_cast<uint32_t*>(v));
           tmem_wait_ld();
@@ -256,71 +331,132 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
         }
         tmem_wait_st();
         fence_before_sync();
-        mbar_arrive(&bars[Y1_FULL]);
+        warp_arrive(&bars[Y1_FULL]);
+        PROF_MARK(9);
         // ---- E7: r1 chunks again for res_1
         mbar_wait(&bars[D0B_FULL], ph);
+        PROF_MARK(10);
         fence_after_sync();
         gen_chunks();
-        // ---- E8: o1 = D4 + b_r1; nabla_V = relu(up_0 o1 + b) + res_0 [t,x] + b; SDE step
+        PROF_MARK(11);
+        // ---- E8: o1 = D4 + b_r1; partial up_0 over this half's 128 columns
         mbar_wait(&bars[D4B_FULL], ph);
+        PROF_MARK(12);
         fence_after_sync();
         float au[KIN];
 #pragma unroll
         for (int j = 0; j < KIN; ++j) au[j] = 0.f;
-        const int dp = ((d + 3) / 4) * 4;
 #pragma unroll 1
-        for (int cb = 0; cb < 8; ++cb) {
-          float v[32];
-          tmem_ld32(lane_t + C_D4 + 32 * cb, reinterpret_cast<uint32_t*>(v));
+        for (int cb = 8 * h; cb < 8 * h + 8; ++cb) {  // 16 columns at a time
+          float v[16];
+          tmem_ld16(lane_t + C_D4 + 16 * cb, reinterpret_cast<uint32_t*>(v));
           tmem_wait_ld();
-          bias32(v, sm_small + so.b_r1 + 32 * cb);
-          const float* wu = sm_small + so.u0t + (32 * cb) * dp;
+          const float* br = sm_small + so.b_r1 + 16 * cb;
+          const float* wu = sm_small + so.u0t + (16 * cb) * KIN;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < 16; ++j) {
+            const float o = v[j] + br[j];
 #pragma unroll
             for (int q = 0; q < KIN / 4; ++q) {
-              if (4 * q < d) {
-                const float4 w = *reinterpret_cast<const float4*>(wu + j * dp + 4 * q);
-                au[4 * q] = fmaf(w.x, v[j], au[4 * q]);
-                au[4 * q + 1] = fmaf(w.y, v[j], au[4 * q + 1]);
-                au[4 * q + 2] = fmaf(w.z, v[j], au[4 * q + 2]);
-                au[4 * q + 3] = fmaf(w.w, v[j], au[4 * q + 3]);
-              }
+              const float4 w = *reinterpret_cast<const float4*>(wu + j * KIN + 4 * q);
+              au[4 * q] = fmaf(w.x, o, au[4 * q]);
+              au[4 * q + 1] = fmaf(w.y, o, au[4 * q + 1]);
+              au[4 * q + 2] = fmaf(w.z, o, au[4 * q + 2]);
+              au[4 * q + 3] = fmaf(w.w, o, au[4 * q + 3]);
             }
           }
         }
         fence_before_sync();  // orders the TMEM reads before the next step's MMAs (via XIN_FULL)
-        if (live) {
-          float gv[kMaxDim], xs[kMaxDim];
-          const float tk = __ldg(a.step_tab + 4 * K + k);
+        PROF_MARK(13);
+        // helpers hand their partial sums and the noise to the owners through the idle chunk buffer
+        if (h == 1) {
 #pragma unroll
           for (int j = 0; j < KIN; ++j) {
-            if (j < d) {
-              const float* wr = sm_small + so.r0 + j * KIN;
-              float ar = sm_small[so.b_r0 + j] + wr[0] * tk;
-#pragma unroll
-              for (int c = 1; c < KIN; ++c)
-                if (c <= d) ar = fmaf(wr[c], x[c - 1], ar);
-              gv[j] = fmaxf(au[j] + sm_small[so.b_u0 + j], 0.f) + ar;
-              xs[j] = x[j];
-            }
+            stage_f[j * TP + p] = au[j];
+            stage_f[(KIN + j) * TP + p] = eps[j];
           }
-          path_step_eps(a, m, k, xs, 1, gv, 1, eps, acc);
-#pragma unroll
-          for (int j = 0; j < KIN; ++j)
-            if (j < d) x[j] = xs[j];
         }
+        e_sync();
+        PROF_MARK(15);
+        if (h == 0 && live) {
+          float gv[KIN], u[KIN];
+          const float tk = __ldg(a.step_tab + 4 * K + k);
+#pragma unroll
+          for (int j = 0; j < KIN; ++j) {  // lanes >= d come out as exact zeros (zero-padded parameters)
+            const float* wr = sm_small + so.r0 + j * KIN;
+            float ar = fmaf(wr[0], tk, sm_small[so.b_r0 + j]);
+#pragma unroll
+            for (int c = 1; c < KIN; ++c) ar = fmaf(wr[c], x[c - 1], ar);
+            gv[j] = fmaxf(au[j] + stage_f[j * TP + p] + sm_small[so.b_u0 + j], 0.f) + ar;
+            eps[j] = stage_f[(KIN + j) * TP + p];
+          }
+          const float dt = __ldg(a.step_tab + k), sq_ldt = __ldg(a.step_tab + K + k);
+          const float dt_l = __ldg(a.step_tab + 2 * K + k), sq_dtl = __ldg(a.step_tab + 3 * K + k);
+          const float* wA = a.warmA ? a.warmA + (size_t)k * d * d : nullptr;
+          const float* wc = a.warmc ? a.warmc + (size_t)k * d : nullptr;
+          float eff;
+          if (diag) {
+            eff = sde_step_diag<KIN>(a.st.kind == SOCM_MOLECULAR_DYNAMICS, a.st.lmbd, kap, x, gv, eps, u, dt, sq_ldt,
+                                     dt_l, sq_dtl, acc);
+          } else {
+            // dense sigma / OU drift / warm start: run-time loops on thread-local arrays
+            float xl[kMaxDim], gl[kMaxDim], el[kMaxDim], ul[kMaxDim];
+#pragma unroll
+            for (int j = 0; j < KIN; ++j)
+              if (j < d) {
+                xl[j] = x[j];
+                gl[j] = gv[j];
+                el[j] = eps[j];
+              }
+            eff = sde_step(a.st, wA, wc, xl, 1, gl, 1, el, ul, dt, sq_ldt, dt_l, sq_dtl, acc);
+#pragma unroll
+            for (int j = 0; j < KIN; ++j)
+              if (j < d) {
+                x[j] = xl[j];
+                u[j] = ul[j];
+              }
+          }
+          const size_t row = (size_t)k * B + m;
+          if (a.states) {
+            float* sp = a.states + (row + B) * d;
+            float* cp = a.controls + row * d;
+#pragma unroll
+            for (int j = 0; j < KIN; ++j)
+              if (j < d) {
+                sp[j] = x[j];
+                cp[j] = u[j];
+              }
+            if (a.noise_in == nullptr) {
+              float* np_ = a.noises + row * d;
+#pragma unroll
+              for (int j = 0; j < KIN; ++j)
+                if (j < d) np_[j] = eps[j];
+            }
+            a.stop[row + B] = acc.alive;
+            a.eff_dt[row] = eff;
+          }
+        }
+        e_sync();  // the exchange area is chunk buffer 0 again from here on
+        PROF_MARK(14);
       }
-      if (live) {
-        float xs[kMaxDim];
+      if (live && h == 0) {
+        a.lw_det[m] = acc.lw_det;
+        a.lw_sto[m] = acc.lw_sto;
+        float xl[kMaxDim];
 #pragma unroll
         for (int j = 0; j < KIN; ++j)
-          if (j < d) xs[j] = x[j];
-        path_finish(a, m, xs, 1, acc);
+          if (j < d) xl[j] = x[j];
+        a.lw_term[m] = __fdiv_rn(-term_cost(a.st, xl, 1), a.st.lmbd);  // utils.py:101
       }
     }
-  } else if (warp == 4) {
+    PROF_FLUSH(0, tid == 0);
+    PROF_FLUSH(32, tid == 128);
+    };  // e_program
+    if (warp < 4) e_program(std::integral_constant<int, 0>{});
+    else e_program(std::integral_constant<int, 1>{});
+  } else if (warp == 8) {
     // =================================================================== M: MMA issue
+    PROF_DECL;
     uint32_t ws = 0;  // weight stages consumed
     uint32_t cm = 0;  // chunks consumed
     uint32_t g = 0;
@@ -338,9 +474,9 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
     };
     auto down0 = [&]() {  // D0 = [t,x] W0^T into columns [0,256)
 #pragma unroll
-      for (int h = 0; h < S0; ++h) {
+      for (int hh = 0; hh < S0; ++hh) {
         const uint32_t wb = wait_w();
-        if (elect_one()) issue_block_ss<H0 / S0, KIN>(tm + C_SA + h * (H0 / S0), xin_s, KIN * 512, wb, true);
+        if (elect_one()) issue_block_ss<H0 / S0, KIN>(tm + C_SA + hh * (H0 / S0), xin_s, KIN * 512, wb, true);
         __syncwarp();
         release_w();
       }
@@ -348,7 +484,9 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
     for (; g < total_steps; ++g) {
       const uint32_t ph = g & 1;
       // ---- M0: down_0
+      PROF_MARK(0);
       mbar_wait(&bars[XIN_FULL], ph);
+      PROF_MARK(1);
       fence_after_sync();
       down0();
       if (elect_one()) commit(&bars[D0_FULL]);
@@ -369,8 +507,10 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
       }
       if (elect_one()) commit(&bars[D1_FULL]);
       __syncwarp();
+      PROF_MARK(2);
       // ---- M2: down_2, A = r2 (TMEM), 2 blocks of K = 64
       mbar_wait(&bars[R2_FULL], ph);
+      PROF_MARK(3);
       fence_after_sync();
       for (int j = 0; j < 2; ++j) {
         const uint32_t wb = wait_w();
@@ -380,8 +520,10 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
       }
       if (elect_one()) commit(&bars[D2_FULL]);
       __syncwarp();
+      PROF_MARK(4);
       // ---- M3: up_2, A = r3 (TMEM), 2 blocks of K = 32
       mbar_wait(&bars[R3_FULL], ph);
+      PROF_MARK(5);
       fence_after_sync();
       for (int j = 0; j < 2; ++j) {
         const uint32_t wb = wait_w();
@@ -391,8 +533,10 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
       }
       if (elect_one()) commit(&bars[D3A_FULL]);
       __syncwarp();
+      PROF_MARK(4);
       // ---- M4: res_2 on top of relu(y2), A = r2 (TMEM), 4 blocks of K = 32
       mbar_wait(&bars[Y2_FULL], ph);
+      PROF_MARK(5);
       fence_after_sync();
       for (int j = 0; j < 4; ++j) {
         const uint32_t wb = wait_w();
@@ -402,8 +546,10 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
       }
       if (elect_one()) commit(&bars[D3B_FULL]);
       __syncwarp();
+      PROF_MARK(4);
       // ---- M5: up_1, A = o2 (TMEM), 8 blocks of K = 16
       mbar_wait(&bars[O2_FULL], ph);
+      PROF_MARK(6);
       fence_after_sync();
       for (int j = 0; j < 8; ++j) {
         const uint32_t wb = wait_w();
@@ -413,14 +559,18 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
       }
       if (elect_one()) commit(&bars[D4A_FULL]);
       __syncwarp();
+      PROF_MARK(7);
       // down_0 again into [0,256) once up_1 has finished reading o2 from there
       mbar_wait(&bars[D4A_FULL], ph);
+      PROF_MARK(8);
       fence_after_sync();
       down0();
       if (elect_one()) commit(&bars[D0B_FULL]);
       __syncwarp();
+      PROF_MARK(9);
       // ---- M6: res_1 on top of relu(y1), A = r1 chunks, 16 blocks of K = 16
       mbar_wait(&bars[Y1_FULL], ph);
+      PROF_MARK(10);
       fence_after_sync();
       for (int c = 0; c < 8; ++c) {
         const uint32_t b = cm & 1;
@@ -439,7 +589,9 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
       }
       if (elect_one()) commit(&bars[D4B_FULL]);
       __syncwarp();
+      PROF_MARK(11);
     }
+    PROF_FLUSH(16, (tid & 31) == 0);
   } else {
     // =================================================================== P: weight tape producer
     if (elect_one()) {
@@ -461,8 +613,14 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
   // ---- teardown: every MMA has completed (E waited for the last D4B_FULL)
   fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tm, 512);
+  if (warp == 8) tmem_dealloc(tm, 512);
 }
+
+#ifdef SOCM_TC_PROF
+extern "C" int socm_debug_tc_prof(unsigned long long* out32) {
+  return (int)cudaMemcpyFromSymbol(out32, g_tc_prof, sizeof(g_tc_prof));
+}
+#endif
 
 int64_t rollout_tc_workspace_bytes(int d) { return tc_workspace_bytes(d); }
 bool rollout_tc_supported(const socm_unet* net) { return is_default_arch(net) && kin_of(net->d) <= MAX_KIN; }

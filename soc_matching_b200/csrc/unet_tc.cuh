@@ -83,14 +83,14 @@ __host__ __device__ inline int fwd_stage_slot(int d, int i) {
 // ---------------------------------------------------------------- small block (floats, fp32, read from shared memory)
 struct SmallTc {
   int b_d0, b_d1, b_d2, b_u2, b_r2, b_u1, b_r1;
-  int u0t;   // up_0^T [256][dp]   (dp = d rounded up to 4)
-  int b_u0;  // [dp]
-  int r0;    // res_0 [d][kin]     (zero padded rows)
-  int b_r0;  // [dp]
+  int u0t;   // up_0^T [256][kin]  (zero padded: the per-point loops run over kin lanes without predicates)
+  int b_u0;  // [kin]
+  int r0;    // res_0 [kin][kin]   (zero padded rows and columns; column 0 multiplies t)
+  int b_r0;  // [kin]
   int total;
 };
 __host__ __device__ inline SmallTc small_tc(int d) {
-  const int dp = ((d + 3) / 4) * 4, kin = kin_of(d);
+  const int kin = kin_of(d);
   SmallTc o;
   int p = 0;
   o.b_d0 = p; p += H0;
@@ -100,10 +100,10 @@ __host__ __device__ inline SmallTc small_tc(int d) {
   o.b_r2 = p; p += H1;
   o.b_u1 = p; p += H0;
   o.b_r1 = p; p += H0;
-  o.u0t = p; p += H0 * dp;
-  o.b_u0 = p; p += dp;
-  o.r0 = p; p += d * kin;
-  o.b_r0 = p; p += dp;
+  o.u0t = p; p += H0 * kin;
+  o.b_u0 = p; p += kin;
+  o.r0 = p; p += kin * kin;
+  o.b_r0 = p; p += kin;
   o.total = ((p + 3) / 4) * 4;
   return o;
 }
@@ -193,6 +193,37 @@ __device__ __forceinline__ void store_chunk32(unsigned char* chunk, int p, const
   unsigned char* base = chunk + (p % 8) * 16 + (p / 8) * 128;
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
+    float4 h, l;
+    h.x = umma::tf32_rn(v[4 * g]);
+    h.y = umma::tf32_rn(v[4 * g + 1]);
+    h.z = umma::tf32_rn(v[4 * g + 2]);
+    h.w = umma::tf32_rn(v[4 * g + 3]);
+    l.x = v[4 * g] - h.x;
+    l.y = v[4 * g + 1] - h.y;
+    l.z = v[4 * g + 2] - h.z;
+    l.w = v[4 * g + 3] - h.w;
+    *reinterpret_cast<float4*>(base + g * 2048) = h;
+    *reinterpret_cast<float4*>(base + CHUNK_HALF + g * 2048) = l;
+  }
+}
+
+
+// 16-column variants (used when two warps share a TMEM lane quarter and split the columns)
+__device__ __forceinline__ void bias_relu16(float* v, const float* __restrict__ bias) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + j);
+    v[j] = fmaxf(v[j] + b.x, 0.f);
+    v[j + 1] = fmaxf(v[j + 1] + b.y, 0.f);
+    v[j + 2] = fmaxf(v[j + 2] + b.z, 0.f);
+    v[j + 3] = fmaxf(v[j + 3] + b.w, 0.f);
+  }
+}
+// 16 features (4 column groups starting at group g0) of point p into a shared-memory A chunk
+__device__ __forceinline__ void store_chunk16(unsigned char* chunk, int p, int g0, const float* v) {
+  unsigned char* base = chunk + (p % 8) * 16 + (p / 8) * 128 + g0 * 2048;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
     float4 h, l;
     h.x = umma::tf32_rn(v[4 * g]);
     h.y = umma::tf32_rn(v[4 * g + 1]);
