@@ -8,7 +8,7 @@ using namespace socm::umma;
 
 // mode 0: A MN-major (decode A), B K-major identity (N=16): D[m][n] = A(m, k=n) n<8
 // mode 1: B MN-major (decode B), A K-major identity: D[m][n] = B(n, k=m) for m<8
-__global__ void __launch_bounds__(128) decode_kernel(int mode, int lbo, int sbo, int N, float* D) {
+__global__ void __launch_bounds__(128) decode_kernel(int mode, int lbo, int sbo, int N, int ltype, float* D) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t slot;
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(128) decode_kernel(int mode, int lbo, int sbo,
   const uint32_t tb = slot;
   if (tid == 0) {
     const uint64_t idd = smem_desc(smem_addr(ident), 128, 256);
-    const uint64_t rd = smem_desc(smem_addr(region), lbo, sbo);
+    const uint64_t rd = smem_desc(smem_addr(region), lbo, sbo) | ((uint64_t)ltype << 61);
     if (mode == 0) mma_ss(tb, rd, idd, idesc_tf32(128, N, 1, 0), 0);
     else mma_ss(tb, idd, rd, idesc_tf32(128, N, 0, 1), 0);
     commit(&bar);
@@ -54,17 +54,17 @@ int main() {
   float* dD; cudaMalloc(&dD, 128 * 256 * 4);
   float* h = (float*)malloc(128 * 256 * 4);
   cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  const int cfgs[][2] = {{4096, 1024}, {1024, 4096}, {2048, 512}};
+  const int cfgs[][3] = {{4096, 1024, 1}, {1024, 4096, 1}, {8192, 512, 1}, {4096, 1024, 2}, {4096, 1024, 6}};
   for (int mode = 0; mode < 2; ++mode)
     for (auto& c : cfgs) {
       const int N = mode == 0 ? 16 : 64;
       cudaMemset(dD, 0, 128 * 256 * 4);
-      decode_kernel<<<1, 128, 200 * 1024>>>(mode, c[0], c[1], N, dD);
+      decode_kernel<<<1, 128, 200 * 1024>>>(mode, c[0], c[1], N, c[2], dD);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
       cudaMemcpy(h, dD, 128 * N * 4, cudaMemcpyDeviceToHost);
-      printf("mode %d (decode %s MN-major) LBO=%d SBO=%d : byte offset read for (mn, k)\n", mode, mode == 0 ? "A" : "B", c[0], c[1]);
-      const int mns[] = {0, 1, 2, 3, 4, 5, 7, 8, 9, 12, 16, 17, 31, 32, 33, 63};
+      printf("mode %d (decode %s MN-major) LBO=%d SBO=%d layout_type=%d : byte offset read for (mn, k)\n", mode, mode == 0 ? "A" : "B", c[0], c[1], c[2]);
+      const int mns[] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 12, 13, 16, 17, 20, 24, 28, 31, 32, 33, 36, 63, 64, 65, 96, 127};
       for (int mn : mns) {
         if (mode == 0 ? mn >= 128 : mn >= N) continue;
         printf("  mn %3d:", mn);

@@ -59,6 +59,11 @@ PROTOTYPES = {
                                             _vp, _i32, _vp, _vp, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _u32, _vp]),
     "socm_weight_stats_f32": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
 }
+# test-only entry points (not part of include/socm_b200.h)
+DEBUG_PROTOTYPES = {
+    "socm_debug_wgrad_tc": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
+    "socm_debug_wgrad_tile_bytes": (_i64, []),
+}
 
 ROLLOUT_FORCE_GENERIC = 1
 ROLLOUT_NO_TRAJ = 2
@@ -83,7 +88,7 @@ def load():
             "(there is no CPU fallback)."
         )
     lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in PROTOTYPES.items():
+    for name, (res, args) in list(PROTOTYPES.items()) + list(DEBUG_PROTOTYPES.items()):
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

@@ -1,0 +1,68 @@
+// loss_tc.cuh -- shared definitions of the tensor-core K3 (loss_tc.cu = K3a: forward + loss + dgrad,
+// wgrad_tc.cu = K3b: weight gradients).
+//
+// K3a hands K3b every operand of the weight-gradient GEMMs  dW[out][in] = sum_p dY[p][out] Act[p][in]
+// through a global scratch in exactly the shared-memory layout tcgen05.mma wants for an MN-major
+// tf32 operand (the only layout the hardware accepts there is SWIZZLE_128B with 32-byte atoms,
+// decoded with scripts/umma_decode.cu):
+//   a "feature block" = 32 consecutive features of one tensor for 32 consecutive points (a TMEM lane
+//   quarter = one warp of K3a) = 32 rows of 128 bytes; row r holds the 32 features of point r with
+//   its four 32-byte units XOR-permuted by (r & 3).  Values are rounded to tf32 (RN) by the writer;
+//   the weight gradient is a single-pass TF32 GEMM with fp32 accumulation over all points, which
+//   keeps the per-tensor error far below the 1e-4 bound (error ~ 2^-12 / sqrt(#points)).
+//   tile (128 points) -> 4 quarters -> NFB feature blocks of 4 KB.
+#pragma once
+#include "common.cuh"
+
+namespace socm {
+namespace tc {
+
+// feature-block index of each tensor inside a quarter
+enum Fb {
+  FB_XIN = 0,   // [t, x_0..x_{d-1}, 0.., 1 at feature 31]
+  FB_R1 = 1,    // 8 blocks
+  FB_R2 = 9,    // 4
+  FB_R3 = 13,   // 2
+  FB_O2 = 15,   // 4
+  FB_O1 = 19,   // 8
+  FB_DY0 = 27,  // d_y0 (features >= d are zero)
+  FB_DO0 = 28,  // d_o0
+  FB_DY1 = 29,  // 8
+  FB_DO1 = 37,  // 8
+  FB_DY2 = 45,  // 4
+  FB_DO2 = 49,  // 4
+  FB_DZ3 = 53,  // 2
+  FB_DZ2 = 55,  // 4
+  FB_DZ1 = 59,  // 8
+  NFB = 67
+};
+constexpr int FB_BYTES = 4096;
+constexpr int QUARTER_BYTES = NFB * FB_BYTES;
+constexpr int64_t TILE_BYTES = 4LL * QUARTER_BYTES;  // 1 097 728
+constexpr int ONES_FEATURE = 31;                     // constant-1 feature of the FB_XIN block (bias gradients)
+constexpr int MAX_D_TC_LOSS = 30;
+
+// byte offset of feature f (0..31) of point-row r (0..31) inside a feature block
+__host__ __device__ inline int fb_off(int r, int f) { return r * 128 + (((f >> 3) ^ (r & 3)) << 5) + (f & 7) * 4; }
+
+// flat gradient layout (= socm_unet layer order, w then b per layer; same as loss_tile.cu)
+struct GradOffTc {
+  int w[9], b[9], total;
+};
+__host__ __device__ inline GradOffTc grad_offsets_tc(int d) {
+  const int nout[9] = {256, 128, 64, d, 256, 128, 128, 256, d};
+  const int nin[9] = {d + 1, 256, 128, d + 1, 256, 128, 64, 128, 256};
+  GradOffTc g;
+  int p = 0;
+  for (int l = 0; l < 9; ++l) {
+    g.w[l] = p;
+    p += nout[l] * nin[l];
+    g.b[l] = p;
+    p += nout[l];
+  }
+  g.total = p;
+  return g;
+}
+
+}  // namespace tc
+}  // namespace socm
