@@ -142,6 +142,9 @@ int socm_target_const_m_f32(const float* R, int32_t B, int32_t K, int32_t d, int
  * stop may be NULL (all ones).  warm: rows = K+1 (rank-3 branch, models.py:184-186) or NULL.
  * workspace: socm_loss_workspace_bytes() bytes.  flags: SOCM_LOSS_FORCE_GENERIC. */
 #define SOCM_LOSS_FORCE_GENERIC 1u
+#define SOCM_LOSS_FORCE_FFMA 2u /* default net: fp32 FFMA tile kernel instead of the tcgen05 kernels */
+#define SOCM_LOSS_FORCE_TC 4u   /* default net: tcgen05 kernels even below SOCM_LOSS_TC_MIN_POINTS */
+#define SOCM_LOSS_TC_MIN_POINTS 65536 /* (K+1)*B from which the tcgen05 kernels are the default */
 int64_t socm_loss_workspace_bytes(const socm_unet* net, int32_t B, int32_t K);
 int64_t socm_unet_param_count(const socm_unet* net);
 int socm_unet_loss_fwdbwd_f32(const socm_setting* st, const socm_unet* net, const socm_warm_table* warm,

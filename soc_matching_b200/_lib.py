@@ -69,6 +69,8 @@ ROLLOUT_FORCE_GENERIC = 1
 ROLLOUT_NO_TRAJ = 2
 ROLLOUT_FORCE_FFMA = 4
 LOSS_FORCE_GENERIC = 1
+LOSS_FORCE_FFMA = 2
+LOSS_FORCE_TC = 4
 
 _lib = None
 

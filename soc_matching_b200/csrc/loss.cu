@@ -37,6 +37,9 @@ __global__ void __launch_bounds__(128) loss_generic_kernel(LossArgs a, socm_unet
 
 int launch_loss_tile(const LossArgs& a, const socm_unet* net, float* grad, void* workspace, cudaStream_t stream);
 int64_t loss_tile_workspace_bytes(int d, int B, int K);
+namespace tc {
+int launch_loss_tc(const LossArgs& a, const socm_unet* net, float* grad, void* workspace, cudaStream_t stream);
+}
 
 }  // namespace socm
 
@@ -45,7 +48,11 @@ using namespace socm;
 
 extern "C" int64_t socm_loss_workspace_bytes(const socm_unet* net, int32_t B, int32_t K) {
   if (!net) return -1;
-  if (is_default_arch(net)) return loss_tile_workspace_bytes(net->d, B, K);
+  if (is_default_arch(net)) {
+    const int64_t ffma = loss_tile_workspace_bytes(net->d, B, K);
+    const int64_t tcb = tc::loss_tc_supported(net) ? tc::loss_tc_workspace_bytes(net->d, B, K) : 0;
+    return ffma > tcb ? ffma : tcb;
+  }
   return 256;  // the generic kernel needs no workspace
 }
 
@@ -76,7 +83,13 @@ extern "C" int socm_unet_loss_fwdbwd_f32(const socm_setting* st, const socm_unet
   a.ldt = ldt;
   a.G = G;
   a.loss_sums = loss_sums;
-  if (is_default_arch(net) && !(flags & 1u)) return launch_loss_tile(a, net, grad, workspace, stream);
+  // tcgen05 kernels for large batches; the fp32 FFMA tile kernel below that (the
+  // 3xTF32 forward differs from fp32 by ~2e-6, enough to flip a ReLU mask about once per 5e5
+  // pre-activations, which is visible in the gradients of small problems)
+  const bool want_tc = (flags & SOCM_LOSS_FORCE_TC) || (int64_t)(K + 1) * B >= SOCM_LOSS_TC_MIN_POINTS;
+  if (tc::loss_tc_supported(net) && want_tc && !(flags & (SOCM_LOSS_FORCE_GENERIC | SOCM_LOSS_FORCE_FFMA)))
+    return tc::launch_loss_tc(a, net, grad, workspace, stream);
+  if (is_default_arch(net) && !(flags & SOCM_LOSS_FORCE_GENERIC)) return launch_loss_tile(a, net, grad, workspace, stream);
   const int warps = 4;
   const size_t smem = (size_t)warps *
                       (generic::fwd_floats(st->d, net->h0, net->h1, net->h2) +

@@ -1,0 +1,714 @@
+// loss_tc.cu -- K3a: UNet forward at 128 trajectory points, weighted loss and the whole dgrad chain
+// on the 5th-gen tensor cores (tcgen05, 3xTF32; engine of unet_tc.cuh), one persistent CTA per SM.
+// Replaces method.py:272-287 (nabla_V at all points), 692-720 (loss) and the activation-gradient
+// half of loss.backward() (main.py:323).  The weight gradients are K3b (wgrad_tc.cu): this kernel
+// leaves every operand they need -- activations and activation gradients, fp32 -- in the scratch
+// layout of loss_tc.cuh.
+//
+// A tile is 128 consecutive paths at one grid time t_i.  Per tile:
+//   forward   exactly the rollout's forward (rollout_tc.cu) from the stored state, keeping the ReLU
+//             masks in registers (thread <-> point, fixed column ownership);
+//   loss      per point: diff = nabla_V - target, loss += s w |sigma^T diff|^2, G = -d loss / d nabla_V;
+//   backward  the mirror image of the forward with the transposed weight tape:
+//               d_o1 = W_u0^T d_y0            (chunk source in TMEM, like down_0)
+//               d_o2 = W_u1^T (m_y1 . d_o1)   (A = 32-feature chunks in shared memory, like down_1)
+//               d_r2 = W_r2^T d_o2 + W_d2^T (m_r3 . W_u2^T (m_y2 . d_o2))
+//               d_r1 = W_d1^T (m_r2 . d_r2) + W_r1^T d_o1
+//               d_z1 = m_r1 . d_r1
+// TMEM columns (backward): [0,256) d_o1 accumulator / A operands (hi|lo);  [256,384) d_o2 acc, later
+// [256,320) d_r3 acc;  [384,512) d_r2 acc;  [256,512) d_r1 acc.
+#include <type_traits>
+
+#include "kernels.h"
+#include "loss_common.cuh"
+#include "loss_tc.cuh"
+#include "unet_tc.cuh"
+
+namespace socm {
+namespace tc {
+
+using namespace umma;
+
+namespace k3 {
+constexpr int SM_RING = 0;
+constexpr int SM_CHUNK = SM_RING + NSTAGE * SLOT_BYTES;
+constexpr int SM_XIN = SM_CHUNK + 2 * CHUNK_BYTES;  // [t,x] operand (forward) / d_y0 operand (backward)
+constexpr int SM_SMALL = SM_XIN + MAX_KIN * 1024;
+enum Bar {
+  W_FULL = 0, W_EMPTY = W_FULL + NSTAGE, CH_FULL = W_EMPTY + NSTAGE, CH_EMPTY = CH_FULL + 2,
+  // forward, one completion per tile each
+  XIN_FULL = CH_EMPTY + 2, D0_FULL, D1_FULL, R2_FULL, D2_FULL, R3_FULL, D3A_FULL, Y2_FULL, D3B_FULL, O2_FULL,
+  D4A_FULL, D0B_FULL, Y1_FULL, D4B_FULL,
+  // backward
+  DY0_FULL, BD0_FULL, BDO2_FULL, BO2_FULL, BR2A_FULL, BY2_FULL, BD3_FULL, BZ3_FULL, BR2B_FULL, BZ2_FULL,
+  BD1A_FULL, BD0B_FULL, BD1B_FULL, N_BARS
+};
+constexpr int NT = 320, NE = 256;
+constexpr uint32_t C_SA = 0, C_D1 = 256, C_D2 = 256, C_D3 = 256, C_R3 = 384, C_D4 = 256;
+constexpr uint32_t C_DO2 = 256, C_DR2 = 384, C_DR3 = 256, C_DR1 = 256;
+}  // namespace k3
+
+__host__ __device__ inline int loss_tc_smem_bytes(int d) {
+  return k3::SM_SMALL + small_tc(d).total * 4 + k3::N_BARS * 8 + 16;
+}
+
+// 16 consecutive features [f0, f0+16) (f0 = 0 or 16) of point-row r into feature block `blk` (plain fp32)
+__device__ __forceinline__ void store_fb16(unsigned char* blk, int r, int f0, const float* v) {
+  unsigned char* row = blk + r * 128;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int f = f0 + 4 * q;
+    *reinterpret_cast<float4*>(row + (((f >> 3) ^ (r & 3)) << 5) + (f & 7) * 4) =
+        make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+}
+__device__ __forceinline__ void store_fb32(unsigned char* blk, int r, const float* v) {
+  store_fb16(blk, r, 0, v);
+  store_fb16(blk, r, 16, v + 16);
+}
+template <int NV>
+__device__ __forceinline__ uint32_t positive_bits(const float* v) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) m |= (v[j] > 0.f ? 1u : 0u) << j;
+  return m;
+}
+template <int NV>
+__device__ __forceinline__ void apply_bits(float* v, uint32_t m) {
+#pragma unroll
+  for (int j = 0; j < NV; ++j) v[j] = ((m >> j) & 1u) ? v[j] : 0.f;
+}
+__device__ __forceinline__ void store_split16(uint32_t a_hi, uint32_t a_lo, const float* v) {
+  uint32_t h[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) h[j] = __float_as_uint(tf32_rn(v[j]));
+  tmem_st16(a_hi, h);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) h[j] = __float_as_uint(v[j] - __uint_as_float(h[j]));
+  tmem_st16(a_lo, h);
+}
+
+template <int KIN>
+__global__ void __launch_bounds__(k3::NT, 1)
+    loss_tc_kernel(LossArgs a, const unsigned char* __restrict__ tape, const float* __restrict__ small_g,
+                   unsigned char* __restrict__ scratch, int tile0, int n_tiles_launch) {
+  using namespace k3;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int d = a.st.d, K = a.K, B = a.B;
+  const SmallTc so = small_tc(d);
+  float* sm_small = reinterpret_cast<float*>(smem + SM_SMALL);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_SMALL + so.total * 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + N_BARS);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n_mblk = (B + TP - 1) / TP;
+  const int my_tiles = (n_tiles_launch - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const bool simple_loss = a.st.sigma_is_identity && a.warmA == nullptr;
+  constexpr int S0 = KIN > 16 ? 2 : 1;
+  constexpr int NSF = 40 + 2 * S0;  // forward weight stages per tile
+  constexpr int NSB = 40 + 2 * S0;  // backward weight stages per tile
+  (void)K;
+
+  for (int i = tid; i < so.total; i += NT) sm_small[i] = __ldg(small_g + i);
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&bars[W_FULL + s], 1);
+      mbar_init(&bars[W_EMPTY + s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars[CH_FULL + b], NE / 32);
+      mbar_init(&bars[CH_EMPTY + b], 1);
+    }
+    mbar_init(&bars[XIN_FULL], TP / 32);
+    mbar_init(&bars[DY0_FULL], TP / 32);
+    const int e2m[] = {R2_FULL, R3_FULL, Y2_FULL, O2_FULL, Y1_FULL, BO2_FULL, BY2_FULL, BZ3_FULL, BZ2_FULL};
+    for (int i = 0; i < 9; ++i) mbar_init(&bars[e2m[i]], NE / 32);
+    const int m2e[] = {D0_FULL, D1_FULL, D2_FULL, D3A_FULL, D3B_FULL, D4A_FULL, D0B_FULL, D4B_FULL, BD0_FULL,
+                       BDO2_FULL, BR2A_FULL, BD3_FULL, BR2B_FULL, BD1A_FULL, BD0B_FULL, BD1B_FULL};
+    for (int i = 0; i < 16; ++i) mbar_init(&bars[m2e[i]], 1);
+    mbar_init_fence();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tm = *tmem_slot;
+  const uint32_t ring_s = smem_addr(smem + SM_RING), chunk_s = smem_addr(smem + SM_CHUNK), xin_s = smem_addr(smem + SM_XIN);
+
+  if (warp < 8) {
+    // =================================================================== E: epilogue / point threads
+    auto e_program = [&](auto h_const) {
+      constexpr int h = decltype(h_const)::value;  // column half; h == 0 threads own the point
+      const int p = tid & (TP - 1), r = tid & 31, q = (tid >> 5) & 3;
+      const uint32_t lane_t = tm + ((uint32_t)(q * 32) << 16);
+      uint32_t g = 0;   // tiles done
+      uint32_t cu = 0;  // chunks produced
+      float* xin_hi = reinterpret_cast<float*>(smem + SM_XIN);
+      float* xin_lo = reinterpret_cast<float*>(smem + SM_XIN + KIN * 512);
+      float* stage_f = reinterpret_cast<float*>(smem + SM_CHUNK);
+      double loss_acc = 0.0;
+
+      for (int lt = blockIdx.x; lt < n_tiles_launch; lt += gridDim.x, ++g) {
+        const int t = tile0 + lt;
+        const int ti = t / n_mblk, m0 = (t - ti * n_mblk) * TP;
+        const int m = m0 + p;
+        const bool live = m < B;
+        const uint32_t ph = g & 1;
+        unsigned char* sq = scratch + (size_t)lt * TILE_BYTES + (size_t)q * QUARTER_BYTES;  // this warp's quarter
+        uint32_t m_r1[8], m_r2[2], m_r3 = 0, m_y2[2], m_y1[8];
+        float x[KIN];
+
+        // chunk producer: v(16 cols) = f(D0 columns) -> shared-memory A chunk; `fn` post-processes the 16 values
+        auto chunks = [&](auto&& fn) {
+          for (int c = 0; c < 8; ++c) {
+            const int b = cu & 1;
+            mbar_wait(&bars[CH_EMPTY + b], ((cu >> 1) & 1) ^ 1);
+            float v[16];
+            tmem_ld16(lane_t + C_SA + 32 * c + 16 * h, reinterpret_cast<uint32_t*>(v));
+            tmem_wait_ld();
+            fn(c, v);
+            store_chunk16(smem + SM_CHUNK + b * CHUNK_BYTES, p, 4 * h, v);
+            fence_async_smem();
+            warp_arrive(&bars[CH_FULL + b]);
+            ++cu;
+          }
+        };
+
+        // ---- F0 (owners): state -> input operand (hi / lo) and the XIN block of the scratch
+        if (h == 0) {
+          const float tk = __ldg(a.ts + ti);
+#pragma unroll
+          for (int j = 0; j < KIN; ++j)
+            x[j] = (j < d && live) ? __ldg(a.states + ((size_t)ti * B + m) * d + j) : 0.f;
+          float xb[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) xb[c] = 0.f;
+          xb[0] = tk;
+#pragma unroll
+          for (int c = 1; c < KIN; ++c) xb[c] = x[c - 1];
+          xb[ONES_FEATURE] = 1.0f;
+#pragma unroll
+          for (int c4 = 0; c4 < KIN / 4; ++c4) {
+            float4 hh, ll;
+            hh.x = tf32_rn(xb[4 * c4]); hh.y = tf32_rn(xb[4 * c4 + 1]); hh.z = tf32_rn(xb[4 * c4 + 2]); hh.w = tf32_rn(xb[4 * c4 + 3]);
+            ll.x = xb[4 * c4] - hh.x; ll.y = xb[4 * c4 + 1] - hh.y; ll.z = xb[4 * c4 + 2] - hh.z; ll.w = xb[4 * c4 + 3] - hh.w;
+            const int off = (p % 8) * 4 + (p / 8) * 32 + c4 * 512;
+            *reinterpret_cast<float4*>(xin_hi + off) = hh;
+            *reinterpret_cast<float4*>(xin_lo + off) = ll;
+          }
+          fence_async_smem();
+          warp_arrive(&bars[XIN_FULL]);
+          store_fb32(sq + FB_XIN * FB_BYTES, r, xb);
+        }
+        // ---- F1: r1 chunks for down_1 (+ mask, + scratch)
+        mbar_wait(&bars[D0_FULL], ph);
+        fence_after_sync();
+        chunks([&](int c, float* v) {
+          bias_relu16(v, sm_small + so.b_d0 + 32 * c + 16 * h);
+          m_r1[c] = positive_bits<16>(v);
+          store_fb16(sq + (FB_R1 + c) * FB_BYTES, r, 16 * h, v);
+        });
+        // ---- F2: r2
+        mbar_wait(&bars[D1_FULL], ph);
+        fence_after_sync();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int cb = 2 * h + i;
+          float v[32];
+          tmem_ld32(lane_t + C_D1 + 32 * cb, reinterpret_cast<uint32_t*>(v));
+          tmem_wait_ld();
+          bias_relu32(v, sm_small + so.b_d1 + 32 * cb);
+          m_r2[i] = positive_bits<32>(v);
+          store_split32(lane_t + C_SA + 32 * cb, lane_t + C_SA + 128 + 32 * cb, v);
+          store_fb32(sq + (FB_R2 + cb) * FB_BYTES, r, v);
+        }
+        tmem_wait_st();
+        fence_before_sync();
+        warp_arrive(&bars[R2_FULL]);
+        // ---- F3: r3
+        mbar_wait(&bars[D2_FULL], ph);
+        fence_after_sync();
+        {
+          float v[32];
+          tmem_ld32(lane_t + C_D2 + 32 * h, reinterpret_cast<uint32_t*>(v));
+          tmem_wait_ld();
+          bias_relu32(v, sm_small + so.b_d2 + 32 * h);
+          m_r3 = positive_bits<32>(v);
+          store_split32(lane_t + C_R3 + 32 * h, lane_t + C_R3 + 64 + 32 * h, v);
+          store_fb32(sq + (FB_R3 + h) * FB_BYTES, r, v);
+        }
+        tmem_wait_st();
+        fence_before_sync();
+        warp_arrive(&bars[R3_FULL]);
+        // ---- F4: y2 = relu(D3 + b_u2) in place
+        mbar_wait(&bars[D3A_FULL], ph);
+        fence_after_sync();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int cb = 2 * h + i;
+          float v[32];
+          tmem_ld32(lane_t + C_D3 + 32 * cb, reinterpret_cast<uint32_t*>(v));
+          tmem_wait_ld();
+          bias_relu32(v, sm_small + so.b_u2 + 32 * cb);
+          m_y2[i] = positive_bits<32>(v);
+          tmem_st32(lane_t + C_D3 + 32 * cb, reinterpret_cast<const uint32_t*>(v));
+        }
+        tmem_wait_st();
+        fence_before_sync();
+        warp_arrive(&bars[Y2_FULL]);
+        // ---- F5: o2
+        mbar_wait(&bars[D3B_FULL], ph);
+        fence_after_sync();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int cb = 2 * h + i;
+          float v[32];
+          tmem_ld32(lane_t + C_D3 + 32 * cb, reinterpret_cast<uint32_t*>(v));
+          tmem_wait_ld();
+          bias32(v, sm_small + so.b_r2 + 32 * cb);
+          store_split32(lane_t + C_SA + 32 * cb, lane_t + C_SA + 128 + 32 * cb, v);
+          store_fb32(sq + (FB_O2 + cb) * FB_BYTES, r, v);
+        }
+        tmem_wait_st();
+        fence_before_sync();
+        warp_arrive(&bars[O2_FULL]);
+        // ---- F6: y1 = relu(D4 + b_u1) in place, chunk-style column ownership (16 columns of every 32)
+        mbar_wait(&bars[D4A_FULL], ph);
+        fence_after_sync();
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          float v[16];
+          tmem_ld16(lane_t + C_D4 + 32 * c + 16 * h, reinterpret_cast<uint32_t*>(v));
+          tmem_wait_ld();
+          bias_relu16(v, sm_small + so.b_u1 + 32 * c + 16 * h);
+          m_y1[c] = positive_bits<16>(v);
+          tmem_st16(lane_t + C_D4 + 32 * c + 16 * h, reinterpret_cast<const uint32_t*>(v));
+        }
+        tmem_wait_st();
+        fence_before_sync();
+        warp_arrive(&bars[Y1_FULL]);
+        // ---- F7: r1 chunks again for res_1
+        mbar_wait(&bars[D0B_FULL], ph);
+        fence_after_sync();
+        chunks([&](int c, float* v) { bias_relu16(v, sm_small + so.b_d0 + 32 * c + 16 * h); });
+        // ---- F8: o1 = D4 + b_r1 (scratch), partial up_0 over this thread's columns
+        mbar_wait(&bars[D4B_FULL], ph);
+        fence_after_sync();
+        float au[KIN];
+#pragma unroll
+        for (int j = 0; j < KIN; ++j) au[j] = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          float v[16];
+          tmem_ld16(lane_t + C_D4 + 32 * c + 16 * h, reinterpret_cast<uint32_t*>(v));
+          tmem_wait_ld();
+          const float* br = sm_small + so.b_r1 + 32 * c + 16 * h;
+          const float* wu = sm_small + so.u0t + (32 * c + 16 * h) * KIN;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            v[j] += br[j];
+#pragma unroll
+            for (int qq = 0; qq < KIN / 4; ++qq) {
+              const float4 w = *reinterpret_cast<const float4*>(wu + j * KIN + 4 * qq);
+              au[4 * qq] = fmaf(w.x, v[j], au[4 * qq]);
+              au[4 * qq + 1] = fmaf(w.y, v[j], au[4 * qq + 1]);
+              au[4 * qq + 2] = fmaf(w.z, v[j], au[4 * qq + 2]);
+              au[4 * qq + 3] = fmaf(w.w, v[j], au[4 * qq + 3]);
+            }
+          }
+          store_fb16(sq + (FB_O1 + c) * FB_BYTES, r, 16 * h, v);
+        }
+        fence_before_sync();
+        if (h == 1) {
+#pragma unroll
+          for (int j = 0; j < KIN; ++j) stage_f[j * TP + p] = au[j];
+        }
+        e_sync();
+        // ---- loss (owners): nabla_V, d loss / d nabla_V, G; d_y0 operand for the backward pass
+        if (h == 0) {
+          float gv[KIN], y0[KIN], dv[KIN];
+          const float tk = __ldg(a.ts + ti);
+#pragma unroll
+          for (int j = 0; j < KIN; ++j) {
+            const float* wr = sm_small + so.r0 + j * KIN;
+            float ar = fmaf(wr[0], tk, sm_small[so.b_r0 + j]);
+#pragma unroll
+            for (int c = 1; c < KIN; ++c) ar = fmaf(wr[c], x[c - 1], ar);
+            y0[j] = au[j] + stage_f[j * TP + p] + sm_small[so.b_u0 + j];
+            gv[j] = fmaxf(y0[j], 0.f) + ar;
+            dv[j] = 0.f;
+          }
+          if (live) {
+            if (simple_loss) {
+              const float* trow = a.target + (size_t)m * a.ldt + (size_t)ti * d;
+              const float s = a.stop ? __ldg(a.stop + (size_t)ti * B + m) : 1.f;
+              const float coef = s * __ldg(a.w + m) * a.scale;
+              float sqs = 0.f;
+              float* grow = a.G + (size_t)m * a.ldt + (size_t)ti * d;
+#pragma unroll
+              for (int j = 0; j < KIN; ++j)
+                if (j < d) {
+                  const float diff = gv[j] - __ldg(trow + j);
+                  sqs = fmaf(diff, diff, sqs);
+                  dv[j] = 2.f * coef * diff;
+                  grow[j] = -dv[j];
+                }
+              loss_acc += (double)(coef * sqs);
+            } else {
+              float xl[kMaxDim], gl[kMaxDim], dl[kMaxDim];
+#pragma unroll
+              for (int j = 0; j < KIN; ++j)
+                if (j < d) {
+                  xl[j] = x[j];
+                  gl[j] = gv[j];
+                }
+              loss_acc += (double)point_loss(a, ti, m, xl, 1, gl, 1, dl);
+#pragma unroll
+              for (int j = 0; j < KIN; ++j)
+                if (j < d) dv[j] = dl[j];
+            }
+          }
+          float dy[32], dz[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) dy[c] = dz[c] = 0.f;
+#pragma unroll
+          for (int j = 0; j < KIN; ++j) {
+            dz[j] = dv[j];                          // d_o0
+            dy[j] = y0[j] > 0.f ? dv[j] : 0.f;      // d_y0
+          }
+          store_fb32(sq + FB_DY0 * FB_BYTES, r, dy);
+          store_fb32(sq + FB_DO0 * FB_BYTES, r, dz);
+#pragma unroll
+          for (int c4 = 0; c4 < KIN / 4; ++c4) {
+            float4 hh, ll;
+            hh.x = tf32_rn(dy[4 * c4]); hh.y = tf32_rn(dy[4 * c4 + 1]); hh.z = tf32_rn(dy[4 * c4 + 2]); hh.w = tf32_rn(dy[4 * c4 + 3]);
+            ll.x = dy[4 * c4] - hh.x; ll.y = dy[4 * c4 + 1] - hh.y; ll.z = dy[4 * c4 + 2] - hh.z; ll.w = dy[4 * c4 + 3] - hh.w;
+            const int off = (p % 8) * 4 + (p / 8) * 32 + c4 * 512;
+            *reinterpret_cast<float4*>(xin_hi + off) = hh;
+            *reinterpret_cast<float4*>(xin_lo + off) = ll;
+          }
+          fence_async_smem();
+          warp_arrive(&bars[DY0_FULL]);
+        }
+        // ---- B1: d_y1 = m_y1 . d_o1 chunks (d_o1, d_y1 -> scratch)
+        mbar_wait(&bars[BD0_FULL], ph);
+        fence_after_sync();
+        chunks([&](int c, float* v) {
+          store_fb16(sq + (FB_DO1 + c) * FB_BYTES, r, 16 * h, v);
+          apply_bits<16>(v, m_y1[c]);
+          store_fb16(sq + (FB_DY1 + c) * FB_BYTES, r, 16 * h, v);
+        });
+        // ---- B2: d_o2 -> A operand; d_o2, d_y2 -> scratch
+        mbar_wait(&bars[BDO2_FULL], ph);
+        fence_after_sync();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int cb = 2 * h + i;
+          float v[32];
+          tmem_ld32(lane_t + C_DO2 + 32 * cb, reinterpret_cast<uint32_t*>(v));
+          tmem_wait_ld();
+          store_split32(lane_t + C_SA + 32 * cb, lane_t + C_SA + 128 + 32 * cb, v);
+          store_fb32(sq + (FB_DO2 + cb) * FB_BYTES, r, v);
+          apply_bits<32>(v, m_y2[i]);
+          store_fb32(sq + (FB_DY2 + cb) * FB_BYTES, r, v);
+        }
+        tmem_wait_st();
+        fence_before_sync();
+        warp_arrive(&bars[BO2_FULL]);
+        // ---- B3: d_y2 -> A operand (once res_2^T has finished reading d_o2)
+        mbar_wait(&bars[BR2A_FULL], ph);
+        fence_after_sync();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int cb = 2 * h + i;
+          float v[32];
+          tmem_ld32(lane_t + C_DO2 + 32 * cb, reinterpret_cast<uint32_t*>(v));
+          tmem_wait_ld();
+          apply_bits<32>(v, m_y2[i]);
+          store_split32(lane_t + C_SA + 32 * cb, lane_t + C_SA + 128 + 32 * cb, v);
+        }
+        tmem_wait_st();
+        fence_before_sync();
+        warp_arrive(&bars[BY2_FULL]);
+        // ---- B4: d_z3 = m_r3 . d_r3 -> A operand [0,64) hi, [64,128) lo
+        mbar_wait(&bars[BD3_FULL], ph);
+        fence_after_sync();
+        {
+          float v[32];
+          tmem_ld32(lane_t + C_DR3 + 32 * h, reinterpret_cast<uint32_t*>(v));
+          tmem_wait_ld();
+          apply_bits<32>(v, m_r3);
+          store_split32(lane_t + C_SA + 32 * h, lane_t + C_SA + 64 + 32 * h, v);
+          store_fb32(sq + (FB_DZ3 + h) * FB_BYTES, r, v);
+        }
+        tmem_wait_st();
+        fence_before_sync();
+        warp_arrive(&bars[BZ3_FULL]);
+        // ---- B5: d_z2 = m_r2 . d_r2 -> A operand
+        mbar_wait(&bars[BR2B_FULL], ph);
+        fence_after_sync();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int cb = 2 * h + i;
+          float v[32];
+          tmem_ld32(lane_t + C_DR2 + 32 * cb, reinterpret_cast<uint32_t*>(v));
+          tmem_wait_ld();
+          apply_bits<32>(v, m_r2[i]);
+          store_split32(lane_t + C_SA + 32 * cb, lane_t + C_SA + 128 + 32 * cb, v);
+          store_fb32(sq + (FB_DZ2 + cb) * FB_BYTES, r, v);
+        }
+        tmem_wait_st();
+        fence_before_sync();
+        warp_arrive(&bars[BZ2_FULL]);
+        // ---- B6: d_o1 chunks (unmasked) for res_1^T
+        mbar_wait(&bars[BD0B_FULL], ph);
+        fence_after_sync();
+        chunks([&](int, float*) {});
+        // ---- B7: d_z1 = m_r1 . d_r1 -> scratch
+        mbar_wait(&bars[BD1B_FULL], ph);
+        fence_after_sync();
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          float v[16];
+          tmem_ld16(lane_t + C_DR1 + 32 * c + 16 * h, reinterpret_cast<uint32_t*>(v));
+          tmem_wait_ld();
+          apply_bits<16>(v, m_r1[c]);
+          store_fb16(sq + (FB_DZ1 + c) * FB_BYTES, r, 16 * h, v);
+        }
+        fence_before_sync();  // TMEM reads done before the next tile's MMAs (ordered through XIN_FULL / e_sync)
+        e_sync();
+      }
+      // ---- loss: warp-shuffle reduction, one fp64 atomic per owner warp
+      if (h == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
+        if ((tid & 31) == 0 && loss_acc != 0.0) atomicAdd(a.loss_sums, loss_acc);
+      }
+    };  // e_program
+    if (warp < 4) e_program(std::integral_constant<int, 0>{});
+    else e_program(std::integral_constant<int, 1>{});
+  } else if (warp == 8) {
+    // =================================================================== M: MMA issue
+    uint32_t ws = 0, cm = 0;
+    auto wait_w = [&]() -> uint32_t {
+      const uint32_t s = ws % NSTAGE;
+      mbar_wait(&bars[W_FULL + s], (ws / NSTAGE) & 1);
+      fence_after_sync();
+      return ring_s + s * SLOT_BYTES;
+    };
+    auto release_w = [&]() {
+      if (elect_one()) commit(&bars[W_EMPTY + ws % NSTAGE]);
+      __syncwarp();
+      ++ws;
+    };
+    auto signal = [&](int bar) {
+      if (elect_one()) commit(&bars[bar]);
+      __syncwarp();
+    };
+    auto wait_e = [&](int bar, uint32_t ph) {
+      mbar_wait(&bars[bar], ph);
+      fence_after_sync();
+    };
+    auto small_k = [&]() {  // [0,256) = (SMEM operand [128 x KIN]) x (first tape block(s)): down_0 / up_0^T
+#pragma unroll
+      for (int hh = 0; hh < S0; ++hh) {
+        const uint32_t wb = wait_w();
+        if (elect_one()) issue_block_ss<H0 / S0, KIN>(tm + C_SA + hh * (H0 / S0), xin_s, KIN * 512, wb, true);
+        __syncwarp();
+        release_w();
+      }
+    };
+    // A = 8 shared-memory chunks of 32 features; one block of K = 32 (N = 128) or two of K = 16 (N = 256) per chunk
+    auto chunk_layer_128 = [&](uint32_t d_col, bool fresh) {
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t b = cm & 1;
+        mbar_wait(&bars[CH_FULL + b], (cm >> 1) & 1);
+        fence_after_sync();
+        const uint32_t wb = wait_w();
+        if (elect_one()) {
+          issue_block_ss<H1, 32>(tm + d_col, chunk_s + b * CHUNK_BYTES, CHUNK_HALF, wb, fresh && c == 0);
+          commit(&bars[CH_EMPTY + b]);
+        }
+        __syncwarp();
+        release_w();
+        ++cm;
+      }
+    };
+    auto chunk_layer_256 = [&](uint32_t d_col) {
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t b = cm & 1;
+        mbar_wait(&bars[CH_FULL + b], (cm >> 1) & 1);
+        fence_after_sync();
+        for (int j = 0; j < 2; ++j) {
+          const uint32_t wb = wait_w();
+          if (elect_one()) {
+            issue_block_ss<H0, 16>(tm + d_col, chunk_s + b * CHUNK_BYTES + j * 2 * ACT_KSTEP, CHUNK_HALF, wb, false);
+            if (j == 1) commit(&bars[CH_EMPTY + b]);
+          }
+          __syncwarp();
+          release_w();
+        }
+        ++cm;
+      }
+    };
+    for (uint32_t g = 0; g < (uint32_t)my_tiles; ++g) {
+      const uint32_t ph = g & 1;
+      // ================= forward
+      wait_e(XIN_FULL, ph);
+      small_k();
+      signal(D0_FULL);
+      chunk_layer_128(C_D1, true);  // down_1
+      signal(D1_FULL);
+      wait_e(R2_FULL, ph);          // down_2: A = r2 (TMEM)
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t wb = wait_w();
+        if (elect_one()) issue_block_ts<H2, 64>(tm + C_D2, tm + C_SA + 64 * j, tm + C_SA + 128 + 64 * j, wb, j == 0);
+        __syncwarp();
+        release_w();
+      }
+      signal(D2_FULL);
+      wait_e(R3_FULL, ph);          // up_2: A = r3
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t wb = wait_w();
+        if (elect_one()) issue_block_ts<H1, 32>(tm + C_D3, tm + C_R3 + 32 * j, tm + C_R3 + 64 + 32 * j, wb, j == 0);
+        __syncwarp();
+        release_w();
+      }
+      signal(D3A_FULL);
+      wait_e(Y2_FULL, ph);          // res_2 on top of relu(y2): A = r2
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t wb = wait_w();
+        if (elect_one()) issue_block_ts<H1, 32>(tm + C_D3, tm + C_SA + 32 * j, tm + C_SA + 128 + 32 * j, wb, false);
+        __syncwarp();
+        release_w();
+      }
+      signal(D3B_FULL);
+      wait_e(O2_FULL, ph);          // up_1: A = o2
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t wb = wait_w();
+        if (elect_one()) issue_block_ts<H0, 16>(tm + C_D4, tm + C_SA + 16 * j, tm + C_SA + 128 + 16 * j, wb, j == 0);
+        __syncwarp();
+        release_w();
+      }
+      signal(D4A_FULL);
+      wait_e(D4A_FULL, ph);         // up_1 has finished reading o2: down_0 again into [0,256)
+      small_k();
+      signal(D0B_FULL);
+      wait_e(Y1_FULL, ph);          // res_1 on top of relu(y1): A = r1 chunks
+      chunk_layer_256(C_D4);
+      signal(D4B_FULL);
+      // ================= backward
+      wait_e(DY0_FULL, ph);         // d_o1 = d_y0 W_u0 into [0,256)
+      small_k();
+      signal(BD0_FULL);
+      chunk_layer_128(C_DO2, true);  // d_o2 = d_y1 W_u1
+      signal(BDO2_FULL);
+      wait_e(BO2_FULL, ph);          // d_r2 = d_o2 W_r2
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t wb = wait_w();
+        if (elect_one()) issue_block_ts<H1, 32>(tm + C_DR2, tm + C_SA + 32 * j, tm + C_SA + 128 + 32 * j, wb, j == 0);
+        __syncwarp();
+        release_w();
+      }
+      signal(BR2A_FULL);
+      wait_e(BY2_FULL, ph);          // d_r3 = d_y2 W_u2  (N = 64)
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t wb = wait_w();
+        if (elect_one()) issue_block_ts<H2, 64>(tm + C_DR3, tm + C_SA + 64 * j, tm + C_SA + 128 + 64 * j, wb, j == 0);
+        __syncwarp();
+        release_w();
+      }
+      signal(BD3_FULL);
+      wait_e(BZ3_FULL, ph);          // d_r2 += d_z3 W_d2  (K = 64: A hi [0,64), lo [64,128))
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t wb = wait_w();
+        if (elect_one()) issue_block_ts<H1, 32>(tm + C_DR2, tm + C_SA + 32 * j, tm + C_SA + 64 + 32 * j, wb, false);
+        __syncwarp();
+        release_w();
+      }
+      signal(BR2B_FULL);
+      wait_e(BZ2_FULL, ph);          // d_r1 = d_z2 W_d1  (N = 256)
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t wb = wait_w();
+        if (elect_one()) issue_block_ts<H0, 16>(tm + C_DR1, tm + C_SA + 16 * j, tm + C_SA + 128 + 16 * j, wb, j == 0);
+        __syncwarp();
+        release_w();
+      }
+      signal(BD1A_FULL);
+      wait_e(BD1A_FULL, ph);         // d_z2 has been read: d_o1 again into [0,256)
+      small_k();
+      signal(BD0B_FULL);
+      chunk_layer_256(C_DR1);        // d_r1 += d_o1 W_r1
+      signal(BD1B_FULL);
+    }
+  } else {
+    // =================================================================== P: weight tape producer (forward then backward tape)
+    if (elect_one()) {
+      const int n_fwd = fwd_slots(d);
+      const uint32_t per_tile = NSF + NSB;
+      const uint32_t total = (uint32_t)my_tiles * per_tile;
+      uint32_t in_tile = 0;
+      for (uint32_t i = 0; i < total; ++i) {
+        const uint32_t s = i % NSTAGE;
+        mbar_wait(&bars[W_EMPTY + s], ((i / NSTAGE) & 1) ^ 1);
+        const bool bwd = in_tile >= (uint32_t)NSF;
+        const int st = bwd ? (int)in_tile - NSF : (int)in_tile;
+        const int slot_in = fwd_stage_slot(d, st);  // same consumption pattern on both tapes
+        const int slot = slot_in + (bwd ? n_fwd : 0);
+        const uint32_t bytes = slot_in < S0 ? (uint32_t)(2 * (H0 / S0) * KIN * 4) : (uint32_t)SLOT_BYTES;
+        mbar_expect_tx(&bars[W_FULL + s], bytes);
+        bulk_g2s(smem + SM_RING + s * SLOT_BYTES, tape + (size_t)slot * SLOT_BYTES, bytes, &bars[W_FULL + s]);
+        if (++in_tile == per_tile) in_tile = 0;
+      }
+    }
+    __syncwarp();
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tm, 512);
+}
+
+// ---------------------------------------------------------------- host side
+constexpr int SUB_TILES_MAX = 8192;  // tiles per K3a/K3b launch pair (scratch = 1.1 MB per tile)
+
+bool loss_tc_supported(const socm_unet* net) { return is_default_arch(net) && kin_of(net->d) <= MAX_KIN; }
+
+static int64_t tape_bytes(int d) { return ((tc_workspace_bytes(d, true) + 1023) / 1024) * 1024; }
+
+int64_t loss_tc_workspace_bytes(int d, int B, int K) {
+  const int64_t n_tiles = (int64_t)(K + 1) * ((B + TP - 1) / TP);
+  const int64_t sub = n_tiles < SUB_TILES_MAX ? n_tiles : SUB_TILES_MAX;
+  return tape_bytes(d) + sub * TILE_BYTES + 1024;
+}
+
+int launch_loss_tc(const LossArgs& a, const socm_unet* net, float* grad, void* workspace, cudaStream_t stream) {
+  const int d = a.st.d;
+  SOCM_CHECK_ARG(workspace != nullptr, "workspace is NULL (socm_loss_workspace_bytes)");
+  unsigned char* tape = static_cast<unsigned char*>(workspace);
+  float* small = reinterpret_cast<float*>(tape + (size_t)2 * fwd_slots(d) * SLOT_BYTES);
+  unsigned char* scratch = tape + tape_bytes(d);
+  scratch += (1024 - (reinterpret_cast<uintptr_t>(scratch) & 1023)) & 1023;
+  if (int rc = pack_tc(net, tape, small, true, stream)) return rc;
+  const int smem = loss_tc_smem_bytes(d);
+  const int n_mblk = (a.B + TP - 1) / TP;
+  const int64_t n_tiles = (int64_t)(a.K + 1) * n_mblk;
+  const int kin = kin_of(d);
+  for (int64_t t0 = 0; t0 < n_tiles; t0 += SUB_TILES_MAX) {
+    const int nt = (int)((n_tiles - t0) < SUB_TILES_MAX ? (n_tiles - t0) : SUB_TILES_MAX);
+    const int grid = nt < sm_count() ? nt : sm_count();
+#define SOCM_LAUNCH_K3(KIN)                                                                               \
+  do {                                                                                                    \
+    SOCM_CUDA(cudaFuncSetAttribute(loss_tc_kernel<KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    loss_tc_kernel<KIN><<<grid, k3::NT, smem, stream>>>(a, tape, small, scratch, (int)t0, nt);            \
+  } while (0)
+    if (kin == 8) SOCM_LAUNCH_K3(8);
+    else if (kin == 16) SOCM_LAUNCH_K3(16);
+    else SOCM_LAUNCH_K3(24);
+#undef SOCM_LAUNCH_K3
+    SOCM_LAUNCH_CHECK();
+    if (int rc = launch_wgrad_tc(scratch, nt, d, grad, stream)) return rc;
+  }
+  return SOCM_OK;
+}
+
+}  // namespace tc
+}  // namespace socm

@@ -7,9 +7,9 @@
 // decoded with scripts/umma_decode.cu):
 //   a "feature block" = 32 consecutive features of one tensor for 32 consecutive points (a TMEM lane
 //   quarter = one warp of K3a) = 32 rows of 128 bytes; row r holds the 32 features of point r with
-//   its four 32-byte units XOR-permuted by (r & 3).  Values are rounded to tf32 (RN) by the writer;
-//   the weight gradient is a single-pass TF32 GEMM with fp32 accumulation over all points, which
-//   keeps the per-tensor error far below the 1e-4 bound (error ~ 2^-12 / sqrt(#points)).
+//   its four 32-byte units XOR-permuted by (r & 3).  Values are plain fp32; K3b splits them into
+//   hi/lo in shared memory and runs the GEMMs as 3xTF32 (a single-pass TF32 weight gradient was
+//   measured at 1e-4 relative error on a 303-point case: not enough margin).
 //   tile (128 points) -> 4 quarters -> NFB feature blocks of 4 KB.
 #pragma once
 #include "common.cuh"

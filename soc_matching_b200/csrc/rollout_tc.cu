@@ -24,18 +24,21 @@ namespace tc {
 using namespace umma;
 
 // ---------------------------------------------------------------- weight repack (once per call)
-__global__ void pack_tc_kernel(socm_unet net, unsigned char* __restrict__ tape, float* __restrict__ small) {
+__global__ void pack_tc_kernel(socm_unet net, unsigned char* __restrict__ tape, float* __restrict__ small,
+                               int with_bwd) {
   const int d = net.d, kin = kin_of(d);
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-  const int n_slots = fwd_slots(d);
+  const int n_fwd = fwd_slots(d), n_slots = with_bwd ? 2 * n_fwd : n_fwd;
   for (int s = 0; s < n_slots; ++s) {
-    const SlotDesc sd = fwd_slot(d, s);
+    const SlotDesc sd = s < n_fwd ? fwd_slot(d, s) : bwd_slot(d, s - n_fwd);
     const float* W = net.w[sd.layer];
     unsigned char* base = tape + (size_t)s * SLOT_BYTES;
     const int slab = sd.N * sd.Kc * 4;
     for (int i = tid; i < sd.N * sd.Kc; i += nth) {
       const int n = i / sd.Kc, k = i - n * sd.Kc;
-      const float w = (sd.k0 + k < sd.ktot) ? W[(size_t)(sd.n0 + n) * sd.ktot + sd.k0 + k] : 0.f;
+      float w = 0.f;
+      if (sd.k0 + k < sd.klim)
+        w = sd.transposed ? W[(size_t)(sd.k0 + k) * sd.ktot + sd.n0 + n] : W[(size_t)(sd.n0 + n) * sd.ktot + sd.k0 + k];
       const float hi = tf32_rn(w);
       const int off = wslab_off(n, k, sd.Kc);
       *reinterpret_cast<float*>(base + off) = hi;
@@ -96,12 +99,6 @@ __device__ unsigned long long g_tc_prof[48];
 // TMEM columns
 constexpr uint32_t C_SA = 0, C_D1 = 256, C_D2 = 256, C_D3 = 256, C_R3 = 384, C_D4 = 256;
 
-// one arrival per warp (the barrier counts warps): every lane's writes are ordered before it by __syncwarp
-__device__ __forceinline__ void warp_arrive(uint64_t* bar) {
-  __syncwarp();
-  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
-}
-__device__ __forceinline__ void e_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the 8 E warps
 
 // eps[0..d) for (path m, step k) into registers: injected or Philox (same draws as draw_noise)
 template <int KIN>
@@ -622,6 +619,12 @@ extern "C" int socm_debug_tc_prof(unsigned long long* out32) {
 }
 #endif
 
+int pack_tc(const socm_unet* net, unsigned char* tape, float* small, bool with_bwd, cudaStream_t stream) {
+  pack_tc_kernel<<<96, 256, 0, stream>>>(*net, tape, small, with_bwd ? 1 : 0);
+  SOCM_LAUNCH_CHECK();
+  return SOCM_OK;
+}
+
 int64_t rollout_tc_workspace_bytes(int d) { return tc_workspace_bytes(d); }
 bool rollout_tc_supported(const socm_unet* net) { return is_default_arch(net) && kin_of(net->d) <= MAX_KIN; }
 
@@ -629,8 +632,7 @@ int launch_rollout_tc(const RolloutArgs& a, const socm_unet* net, void* workspac
   const int d = a.st.d;
   unsigned char* tape = static_cast<unsigned char*>(workspace);
   float* small = reinterpret_cast<float*>(tape + (size_t)fwd_slots(d) * SLOT_BYTES);
-  pack_tc_kernel<<<96, 256, 0, stream>>>(*net, tape, small);
-  SOCM_LAUNCH_CHECK();
+  if (int rc = pack_tc(net, tape, small, false, stream)) return rc;
   const int smem = rollout_tc_smem_bytes(d);
   const int n_tiles = (a.B + TP - 1) / TP;
   const int grid = n_tiles < sm_count() ? n_tiles : sm_count();

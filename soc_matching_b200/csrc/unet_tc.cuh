@@ -48,26 +48,47 @@ __host__ __device__ inline int w0_slots(int d) { return kin_of(d) > 16 ? 2 : 1; 
 // slot order: [down_0 x S] [down_1 x 8] [down_2 x 2] [up_2 x 2] [res_2 x 4] [up_1 x 8] [res_1 x 16]
 struct SlotDesc {
   int layer;  // index into socm_unet::w
-  int n0, N;  // output-feature range of the block
-  int k0, Kc; // input-feature range of the block (Kc multiple of 8)
-  int ktot;   // row length of the nn.Linear weight
+  int n0, N;  // rows of the block (N side of the MMA)
+  int k0, Kc; // contraction range of the block (Kc multiple of 8)
+  int ktot;   // row length of the nn.Linear weight W[out][ktot]
+  int transposed;  // 0: B[n][k] = W[n0+n][k0+k] (forward);  1: B[n][k] = W[k0+k][n0+n] (dgrad: W^T)
+  int klim;   // contraction indices >= klim are zero padding
 };
 __host__ __device__ inline int fwd_slots(int d) { return 40 + w0_slots(d); }
 __host__ __device__ inline SlotDesc fwd_slot(int d, int s) {
   const int S = w0_slots(d), kin = kin_of(d);
-  if (s < S) return SlotDesc{0, s * (H0 / S), H0 / S, 0, kin, d + 1};
+  if (s < S) return SlotDesc{0, s * (H0 / S), H0 / S, 0, kin, d + 1, 0, d + 1};
   s -= S;
-  if (s < 8) return SlotDesc{1, 0, H1, 32 * s, 32, H0};
+  if (s < 8) return SlotDesc{1, 0, H1, 32 * s, 32, H0, 0, H0};
   s -= 8;
-  if (s < 2) return SlotDesc{2, 0, H2, 64 * s, 64, H1};
+  if (s < 2) return SlotDesc{2, 0, H2, 64 * s, 64, H1, 0, H1};
   s -= 2;
-  if (s < 2) return SlotDesc{6, 0, H1, 32 * s, 32, H2};
+  if (s < 2) return SlotDesc{6, 0, H1, 32 * s, 32, H2, 0, H2};
   s -= 2;
-  if (s < 4) return SlotDesc{5, 0, H1, 32 * s, 32, H1};
+  if (s < 4) return SlotDesc{5, 0, H1, 32 * s, 32, H1, 0, H1};
   s -= 4;
-  if (s < 8) return SlotDesc{7, 0, H0, 16 * s, 16, H1};
+  if (s < 8) return SlotDesc{7, 0, H0, 16 * s, 16, H1, 0, H1};
   s -= 8;
-  return SlotDesc{4, 0, H0, 16 * s, 16, H0};
+  return SlotDesc{4, 0, H0, 16 * s, 16, H0, 0, H0};
+}
+// ---- backward (dgrad) tape: W^T blocks in the order the backward pass consumes them
+// [up_0^T x S] [up_1^T x 8] [res_2^T x 4] [up_2^T x 2] [down_2^T x 2] [down_1^T x 8] [res_1^T x 16]
+// (same block shapes as the forward tape, so the same issue code serves both)
+__host__ __device__ inline SlotDesc bwd_slot(int d, int s) {
+  const int S = w0_slots(d), kin = kin_of(d);
+  if (s < S) return SlotDesc{8, s * (H0 / S), H0 / S, 0, kin, H0, 1, d};  // d_o1[f] = sum_j d_y0[j] W_u0[j][f]
+  s -= S;
+  if (s < 8) return SlotDesc{7, 0, H1, 32 * s, 32, H1, 1, H0};   // d_o2[c] = sum_n d_y1[n] W_u1[n][c]
+  s -= 8;
+  if (s < 4) return SlotDesc{5, 0, H1, 32 * s, 32, H1, 1, H1};   // d_r2[c] = sum_n d_o2[n] W_r2[n][c]
+  s -= 4;
+  if (s < 2) return SlotDesc{6, 0, H2, 64 * s, 64, H2, 1, H1};   // d_r3[c] = sum_n d_y2[n] W_u2[n][c]
+  s -= 2;
+  if (s < 2) return SlotDesc{2, 0, H1, 32 * s, 32, H1, 1, H2};   // d_r2[c] += sum_n d_z3[n] W_d2[n][c]
+  s -= 2;
+  if (s < 8) return SlotDesc{1, 0, H0, 16 * s, 16, H0, 1, H1};   // d_r1[c] = sum_n d_z2[n] W_d1[n][c]
+  s -= 8;
+  return SlotDesc{4, 0, H0, 16 * s, 16, H0, 1, H0};              // d_r1[c] += sum_n d_o1[n] W_r1[n][c]
 }
 __host__ __device__ inline int slot_bytes(const SlotDesc& sd) { return 2 * sd.N * sd.Kc * 4; }
 
@@ -107,9 +128,9 @@ __host__ __device__ inline SmallTc small_tc(int d) {
   o.total = ((p + 3) / 4) * 4;
   return o;
 }
-// workspace: [tape: fwd_slots x SLOT_BYTES][small block]
-__host__ __device__ inline int64_t tc_workspace_bytes(int d) {
-  return (int64_t)fwd_slots(d) * SLOT_BYTES + (int64_t)small_tc(d).total * 4;
+// workspace: [tape: fwd_slots (+ fwd_slots backward slots) x SLOT_BYTES][small block]
+__host__ __device__ inline int64_t tc_workspace_bytes(int d, bool with_bwd = false) {
+  return (int64_t)fwd_slots(d) * (with_bwd ? 2 : 1) * SLOT_BYTES + (int64_t)small_tc(d).total * 4;
 }
 
 // canonical no-swizzle K-major offsets (bytes)
@@ -207,6 +228,13 @@ __device__ __forceinline__ void store_chunk32(unsigned char* chunk, int p, const
   }
 }
 
+
+// one arrival per warp (the barrier counts warps): every lane's writes are ordered before it by __syncwarp
+__device__ __forceinline__ void warp_arrive(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) umma::mbar_arrive(bar);
+}
+__device__ __forceinline__ void e_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the 8 epilogue warps
 
 // 16-column variants (used when two warps share a TMEM lane quarter and split the columns)
 __device__ __forceinline__ void bias_relu16(float* v, const float* __restrict__ bias) {

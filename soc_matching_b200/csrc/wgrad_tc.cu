@@ -1,5 +1,5 @@
 // wgrad_tc.cu -- K3b: all weight / bias gradients of the default UNet as tcgen05 GEMMs with the
-// trajectory points as the contraction index (single-pass TF32, fp32 accumulation in TMEM).
+// trajectory points as the contraction index (3xTF32, fp32 accumulation in TMEM).
 //
 //   dW[out][in] += sum_p dY[p][out] * Act[p][in]
 // Operands come from the scratch written by K3a (loss_tc.cuh): both are MN-major (features
@@ -9,7 +9,11 @@
 // TMEM and flushes once with red.global.add -- the flush traffic is negligible and the kernel is
 // bound by streaming the operands from HBM (DESIGN.md, K3b roofline).
 //
-// Warp roles (192 threads): warps 0-3 flush (TMEM -> red.global.add), warp 4 MMA issue, warp 5 producer.
+// The scratch holds plain fp32 values; warps 0-3 split every staged operand in shared memory into
+// hi = rn_tf32(x) (in place) and lo = x - hi (exact, second copy), and each K step issues
+// A_hi*B_hi + A_lo*B_hi + A_hi*B_lo.
+//
+// Warp roles (192 threads): warps 0-3 split + flush (TMEM -> red.global.add), warp 4 MMA issue, warp 5 producer.
 #include "kernels.h"
 #include "loss_tc.cuh"
 #include "umma.cuh"
@@ -48,8 +52,10 @@ __constant__ LayerBlock c_lb[N_LB] = {
     {FB_DZ3, 128, FB_XIN, 32, 0, OUT_BIAS_ONLY, 2, 0},     // rows 0..63 d_z3 -> bias of down_2
 };
 
-constexpr int WG_STAGES = 4;
-constexpr int WG_STAGE_BYTES = 16384 + 32768 + 4096;  // A | B | XIN
+constexpr int WG_STAGES = 2;
+constexpr int WG_RAW_BYTES = 16384 + 32768 + 4096;  // A | B | XIN as copied from the scratch
+constexpr int WG_LO = 53248;                         // offset of the "lo" copy inside a stage
+constexpr int WG_STAGE_BYTES = 2 * 53248;
 constexpr int WG_A = 0, WG_B = 16384, WG_X = 49152;
 constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;  // + alignment slack + barriers
 constexpr int WG_NT = 192;
@@ -67,9 +73,10 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
   // stage bases must be 512-byte aligned in the shared window: the operand swizzle uses address bits 7-8
   unsigned char* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
-  uint64_t* full = bars;                  // [WG_STAGES]
-  uint64_t* empty = bars + WG_STAGES;     // [WG_STAGES]
-  uint64_t* acc_full = bars + 2 * WG_STAGES;
+  uint64_t* full = bars;                  // [WG_STAGES] bulk copies landed
+  uint64_t* empty = bars + WG_STAGES;     // [WG_STAGES] MMAs done reading
+  uint64_t* split = bars + 2 * WG_STAGES; // [WG_STAGES] lo copies written
+  uint64_t* acc_full = bars + 3 * WG_STAGES;
   uint64_t* acc_empty = acc_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -79,6 +86,7 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
     for (int s = 0; s < WG_STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
+      mbar_init(&split[s], 4);
     }
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, 4);
@@ -127,15 +135,23 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
       uint32_t first = 1;
       for (int i = 0; i < my_tiles * 4; ++i, ++it) {
         const uint32_t s = it % WG_STAGES;
-        mbar_wait(&full[s], (it / WG_STAGES) & 1);
+        mbar_wait(&split[s], (it / WG_STAGES) & 1);
         fence_after_sync();
         const uint32_t st = smem_addr(smem + s * WG_STAGE_BYTES);
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = mn_desc(st + WG_A + ks * 1024);
-            mma_ss(tm, ad, mn_desc(st + WG_B + ks * 1024), idesc, (first && ks == 0) ? 0u : 1u);
-            if (lb.with_x) mma_ss(tm + 256, ad, mn_desc(st + WG_X + ks * 1024), idesc_x, (first && ks == 0) ? 0u : 1u);
+            const uint64_t ad = mn_desc(st + WG_A + ks * 1024), al = mn_desc(st + WG_LO + WG_A + ks * 1024);
+            const uint64_t bd = mn_desc(st + WG_B + ks * 1024), bl = mn_desc(st + WG_LO + WG_B + ks * 1024);
+            mma_ss(tm, ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
+            mma_ss(tm, al, bd, idesc, 1u);
+            mma_ss(tm, ad, bl, idesc, 1u);
+            if (lb.with_x) {
+              const uint64_t xd = mn_desc(st + WG_X + ks * 1024), xl = mn_desc(st + WG_LO + WG_X + ks * 1024);
+              mma_ss(tm + 256, ad, xd, idesc_x, (first && ks == 0) ? 0u : 1u);
+              mma_ss(tm + 256, al, xd, idesc_x, 1u);
+              mma_ss(tm + 256, ad, xl, idesc_x, 1u);
+            }
           }
           commit(&empty[s]);
         }
@@ -149,9 +165,34 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
     // ===================================================== flush: TMEM lane r <-> output row of the block
     const uint32_t lane_t = tm + ((uint32_t)(warp * 32) << 16);
     const int r = tid;  // 0..127
+    uint32_t it = 0;
     for (int l = 0; l < N_LB; ++l) {
       const LayerBlock lb = c_lb[l];
       if (my_tiles == 0) break;
+      // ---- split every stage of this layer block: lo = x - trunc_tf32(x)
+      const int a_f4 = lb.M * 8, b_f4 = lb.N * 8;  // float4 counts of the A / B parts (32 points x 4 B per feature)
+      for (int i = 0; i < my_tiles * 4; ++i, ++it) {
+        const uint32_t s = it % WG_STAGES;
+        mbar_wait(&full[s], (it / WG_STAGES) & 1);
+        float4* raw = reinterpret_cast<float4*>(smem + s * WG_STAGE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(smem + s * WG_STAGE_BYTES + WG_LO);
+        auto split_range = [&](int f4_begin, int n_f4) {
+          for (int j = tid; j < n_f4; j += 128) {
+            const float4 x = raw[f4_begin + j];
+            float4 hi, y;
+            hi.x = tf32_rn(x.x); hi.y = tf32_rn(x.y); hi.z = tf32_rn(x.z); hi.w = tf32_rn(x.w);
+            y.x = x.x - hi.x; y.y = x.y - hi.y; y.z = x.z - hi.z; y.w = x.w - hi.w;
+            raw[f4_begin + j] = hi;  // round-to-nearest split (unbiased; the MMA would truncate)
+            lo[f4_begin + j] = y;
+          }
+        };
+        split_range(WG_A / 16, a_f4);
+        split_range(WG_B / 16, b_f4);
+        if (lb.with_x) split_range(WG_X / 16, FB_BYTES / 16);
+        fence_async_smem();
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&split[s]);
+      }
       mbar_wait(acc_full, l & 1);
       fence_after_sync();
       const bool row_ok = true;

@@ -61,6 +61,8 @@ class SOC_Solver(nn.Module):
         self.sigma = neural_sde.sigma if sigma is None else sigma
         self.chunk_paths = 1 << 16
         self.force_generic = False          # tests: run the shape-generic kernels
+        self.force_ffma = False             # tests: fp32 FFMA tile kernels instead of the tcgen05 kernels
+        self.force_tc = False               # tests: tcgen05 K3 even for small batches
         self._injected_noise = None         # tests: (K, B, d) noise replayed by the next loss() call
         self._pair_grid = None
         self.path_offset = 0                # first global path index of this rank (Philox counter)
@@ -183,7 +185,7 @@ class SOC_Solver(nn.Module):
                 noises = self._injected_noise[:, start:start + nb].contiguous()
             simulate.rollout(sde, x0_rep.expand(nb, d).contiguous(), ts, self.lmbd, noises=noises, seed=seed,
                              path_offset=start + self.path_offset, desc=desc, workspace=wsp,
-                             force_generic=self.force_generic, timer=self._timed)
+                             force_generic=self.force_generic, force_ffma=self.force_ffma, timer=self._timed)
             self._timed("prep", 1, lib.socm_target_prep_f32,
                         desc.c_struct, _lib.ptr(wsp.states), _lib.ptr(wsp.noises), _lib.ptr(wsp.controls),
                         _lib.ptr(wsp.eff_dt), wsp.lw[0].data_ptr(), wsp.lw[1].data_ptr(), wsp.lw[2].data_ptr(), nb, K,
@@ -203,7 +205,9 @@ class SOC_Solver(nn.Module):
                         desc.c_struct, udesc, warm_struct, _lib.ptr(ts_f32), _lib.ptr(wsp.states),
                         _lib.ptr(target), ldt, _lib.ptr(wbuf), _lib.ptr(wsp.stop) if stopping else None, scale, nb, K,
                         _lib.ptr(G), _lib.ptr(grad_flat), _lib.ptr(loss_sum), _lib.ptr(loss_ws),
-                        _lib.LOSS_FORCE_GENERIC if self.force_generic else 0, stream)
+                        (_lib.LOSS_FORCE_GENERIC if self.force_generic else 0)
+                        | (_lib.LOSS_FORCE_FFMA if self.force_ffma else 0)
+                        | (_lib.LOSS_FORCE_TC if self.force_tc else 0), stream)
             if L is not None:
                 self._timed("target_bwd", 1, lib.socm_target_gemm_bwd_f32, _lib.ptr(G), _lib.ptr(R), nb, K, d, ldr,
                             ldt, _lib.ptr(dL), 1, stream)

@@ -12,10 +12,12 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def run_product(sde, x0, K, B, lmbd, noises, algo, stopping=False, warm=None, generic=False, chunk=None):
+def run_product(sde, x0, K, B, lmbd, noises, algo, stopping=False, warm=None, generic=False, chunk=None,
+                ffma=False):
     import soc_matching_b200 as sb
     solver = sb.SOC_Solver(sde, x0.to(DEV), None, T=1.0, num_steps=K, lmbd=lmbd, d=sde.dim, sigma=sde.sigma)
     solver.force_generic = generic
+    solver.force_ffma = ffma
     if chunk:
         solver.chunk_paths = chunk
     for p in sde.parameters():
@@ -52,6 +54,13 @@ def test_loss_and_grads_match_reference_golden(name):
                                stopping=m["stopping"], warm=g.warm)
         out, grads = run_product(sde, g.x0, m["K"], m["B"], m["lmbd"], g.traj[1], algo, stopping=m["stopping"],
                                  warm=g.warm)
+        if m["hdims"] == [256, 128, 64]:   # default width runs the tcgen05 kernels: check the FFMA tile path too
+            sde2 = make_product_sde(g.setting, g.unet, g.mnet, g.gammas, m["hdims"], m["hdims_M"], DEV,
+                                    stopping=m["stopping"], warm=g.warm)
+            out2, grads2 = run_product(sde2, g.x0, m["K"], m["B"], m["lmbd"], g.traj[1], algo,
+                                       stopping=m["stopping"], warm=g.warm, ffma=True)
+            assert abs(float(out2[0]) - g.scalar(f"{algo}/loss")) <= 1e-4 * abs(g.scalar(f"{algo}/loss"))
+            check_grads(grads2, g.grads(algo), gamma_tol=2e-3 if m["stopping"] else None)
         want = g.scalar(f"{algo}/loss")
         assert abs(float(out[0]) - want) <= 1e-4 * abs(want), (algo, float(out[0]), want)
         assert abs(float(out[5]) - g.scalar(f"{algo}/weight_mean")) <= 1e-4 * abs(g.scalar(f"{algo}/weight_mean"))
@@ -90,10 +99,13 @@ def test_default_width_matches_oracle(kind, d, K, B, dense, algo):
     if algo == "SOCM":
         want.update({"mnet/" + k: v.grad for k, v in pm.items()})
         want["gam/gamma"] = pg["gamma"].grad
-    for generic in (False, True):
+    # default dispatch (fp32 FFMA tile K3 below SOCM_LOSS_TC_MIN_POINTS; tcgen05 rollout) and shape-generic;
+    # the tcgen05 K3 is covered by tests/test_gpu_loss_tc.py
+    for kernel in ("auto", "ffma", "generic"):
         sde = make_product_sde(st, unet, mnet, gam, hd, hm, DEV)
-        out, grads = run_product(sde, x0, K, B, st.lmbd, noises, algo, generic=generic)
-        assert abs(float(out[0]) - float(obj)) <= 1e-4 * abs(float(obj)), (generic, float(out[0]), float(obj))
+        out, grads = run_product(sde, x0, K, B, st.lmbd, noises, algo, generic=(kernel == "generic"),
+                                 ffma=(kernel == "ffma"))
+        assert abs(float(out[0]) - float(obj)) <= 1e-4 * abs(float(obj)), (kernel, float(out[0]), float(obj))
         assert abs(float(out[5]) - float(wm)) <= 1e-4 * abs(float(wm))
         check_grads(grads, want)
 

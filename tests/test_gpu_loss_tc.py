@@ -1,0 +1,143 @@
+"""tcgen05 K3 (csrc/loss_tc.cu + csrc/wgrad_tc.cu), called through the C ABI with SOCM_LOSS_FORCE_TC.
+
+The forward pass is 3xTF32 (2e-6 from fp32), so a pre-activation that is within ~1e-6 of zero can get
+the other ReLU mask than in the reference -- about one unit in 5e5 -- and that unit's whole gradient
+contribution flips.  The arithmetic check below therefore uses points that are provably away from
+every kink (|pre-activation| > 1e-4 in an fp64 evaluation), where loss and gradients must agree with
+torch fp64 autograd to 2e-5 / 1e-4 (north star: 1e-4); a second test runs the public API end to end."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import make_product_sde, orc, random_setting, rel_l2, seeded_mnet, seeded_unet
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+NAMES = ["down_0", "down_1", "down_2", "res_0", "res_1", "res_2", "up_2", "up_1", "up_0"]
+
+
+def unet64(P, tx):
+    lin = lambda n, v: F.linear(v, P[n + ".0.weight"], P[n + ".0.bias"])  # noqa: E731
+    z1 = lin("down_0", tx); r1 = torch.relu(z1)
+    z2 = lin("down_1", r1); r2 = torch.relu(z2)
+    z3 = lin("down_2", r2); r3 = torch.relu(z3)
+    y2 = lin("up_2", r3); o2 = torch.relu(y2) + lin("res_2", r2)
+    y1 = lin("up_1", o2); o1 = torch.relu(y1) + lin("res_1", r1)
+    y0 = lin("up_0", o1)
+    return torch.relu(y0) + lin("res_0", tx), (z1, z2, z3, y2, y1, y0)
+
+
+@pytest.mark.parametrize("d,K,B", [(10, 40, 300), (1, 30, 129), (20, 9, 200)])
+def test_k3_tc_matches_fp64_autograd_away_from_kinks(d, K, B):
+    from soc_matching_b200 import _lib, networks
+    lib = _lib.load()
+    p = {k: v.to(DEV) for k, v in seeded_unet(d, [256, 128, 64], 31 + d).items()}
+    unet = networks.FullyConnectedUNet(d, (256, 128, 64), 1.0).to(DEV)
+    unet.load_state_dict(p)
+    udesc, keep = networks.unet_desc(unet)
+    g = torch.Generator(DEV).manual_seed(d)
+    ts = torch.linspace(0, 1, K + 1, device=DEV)
+    P = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    states = torch.randn(K + 1, B, d, device=DEV, generator=g)
+    for _ in range(20):   # move every point that sits within 1e-4 of a ReLU kink
+        tx = torch.cat([ts.reshape(-1, 1, 1).expand(K + 1, B, 1), states], -1).double()
+        with torch.no_grad():
+            _, pre = unet64(P, tx)
+        near = torch.stack([(z.abs() < 1e-4).any(-1) for z in pre]).any(0)
+        if not bool(near.any()):
+            break
+        states[near] = torch.randn(int(near.sum()), d, device=DEV, generator=g)
+    assert not bool(near.any())
+    ldt = ((K + 1) * d + 3) // 4 * 4
+    target = torch.randn(B, ldt, device=DEV, generator=g)
+    w = torch.exp(0.3 * torch.randn(B, device=DEV, generator=g))
+    G = torch.zeros(B, ldt, device=DEV)
+    grad = torch.zeros(int(lib.socm_unet_param_count(udesc)), device=DEV)
+    loss = torch.zeros(1, device=DEV, dtype=torch.float64)
+    ws = torch.zeros(int(lib.socm_loss_workspace_bytes(udesc, B, K)) // 4 + 1024, device=DEV)
+    st = _lib.Setting()
+    eye, kap = torch.eye(d, device=DEV), torch.ones(d, device=DEV)
+    st.kind, st.d, st.sigma_is_identity, st.lmbd = 2, d, 1, 1.0
+    st.sigma, st.sigma_inv, st.kappa, st.nu = eye.data_ptr(), eye.data_ptr(), kap.data_ptr(), kap.data_ptr()
+    scale = 1.0 / ((K + 1) * B)
+    _lib.check(lib.socm_unet_loss_fwdbwd_f32(st, udesc, None, ts.data_ptr(), states.data_ptr(), target.data_ptr(),
+                                             ldt, w.data_ptr(), None, scale, B, K, G.data_ptr(), grad.data_ptr(),
+                                             loss.data_ptr(), ws.data_ptr(), _lib.LOSS_FORCE_TC, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    tx = torch.cat([ts.reshape(-1, 1, 1).expand(K + 1, B, 1), states], -1).double()
+    out, _ = unet64(P, tx)
+    out.retain_grad()
+    tgt = target[:, :(K + 1) * d].reshape(B, K + 1, d).permute(1, 0, 2).double()
+    L = (((out - tgt) ** 2).sum(-1) * w.double()[None]).sum() * scale
+    L.backward()
+    assert abs(float(loss) - float(L)) <= 2e-5 * abs(float(L))
+    Gwant = -out.grad.permute(1, 0, 2).reshape(B, (K + 1) * d)           # G = d loss / d target
+    assert rel_l2(G[:, :(K + 1) * d].cpu(), Gwant.cpu()) <= 2e-5
+    o, gc = 0, grad.cpu()
+    for n in NAMES:
+        for suffix in (".0.weight", ".0.bias"):
+            t = P[n + suffix].grad.cpu()
+            got = gc[o:o + t.numel()].reshape(t.shape)
+            o += t.numel()
+            assert rel_l2(got, t) <= 1e-4, (n + suffix, rel_l2(got, t))
+            assert rel_l2(got, t) <= 2e-5, (n + suffix, rel_l2(got, t))   # measured: 2e-6 .. 6e-6
+    del keep
+
+
+@pytest.mark.parametrize("kind,d,K,B", [("double_well", 10, 60, 128), ("ou_quadratic", 20, 12, 40)])
+def test_socm_iteration_with_tc_k3_matches_oracle(kind, d, K, B):
+    """Public API end to end (tcgen05 rollout + tcgen05 K3) against the oracle, loss / gradients 1e-4."""
+    import soc_matching_b200 as sb
+    st = random_setting(kind, d, seed=d + K)
+    hd, hm = [256, 128, 64], [128, 128]
+    unet, mnet = seeded_unet(d, hd, 21 + d), seeded_mnet(d, hm, 22 + d, 0.1)
+    gam = {"gamma": torch.tensor([2.0]), "gamma2": torch.tensor([1.0]), "gamma3": torch.tensor([1.0])}
+    x0 = torch.zeros(d) if kind == "double_well" else 0.3 * torch.ones(d)
+    ts = torch.linspace(0, 1.0, K + 1)
+    noises = torch.randn(K, B, d, generator=torch.Generator().manual_seed(5))
+    torch.set_num_threads(8)
+    traj = orc.rollout(st, unet, x0.repeat(B, 1), ts, noises=noises)
+    pu = {k: v.clone().requires_grad_(True) for k, v in unet.items()}
+    pm = {k: v.clone().requires_grad_(True) for k, v in mnet.items()}
+    pg = {k: v.clone().requires_grad_(True) for k, v in gam.items()}
+    obj, wm, _ = orc.socm_loss(st, pu, pm, pg, ts, traj, algorithm="SOCM")
+    obj.backward()
+    sde = make_product_sde(st, unet, mnet, gam, hd, hm, DEV)
+    solver = sb.SOC_Solver(sde, x0.to(DEV), None, T=1.0, num_steps=K, lmbd=st.lmbd, d=d, sigma=sde.sigma)
+    solver.force_tc = True
+    solver.inject_noise(noises.to(DEV))
+    out = solver.loss(B, algorithm="SOCM")
+    out[0].backward()
+    assert abs(float(out[0].detach()) - float(obj.detach())) <= 1e-4 * abs(float(obj.detach()))
+    for n, prm in sde.nabla_V.named_parameters():
+        assert rel_l2(prm.grad.cpu(), pu[n].grad) <= 1e-4, (n, rel_l2(prm.grad.cpu(), pu[n].grad))
+    for n, prm in sde.M.sigmoid_layers.named_parameters():
+        assert rel_l2(prm.grad.cpu(), pm["sigmoid_layers." + n].grad) <= 1e-4, n
+    assert rel_l2(sde.gamma.grad.cpu(), pg["gamma"].grad) <= 1e-4
+
+
+def test_tc_k3_is_the_default_for_large_batches_and_agrees_with_ffma():
+    """(K+1)*B >= SOCM_LOSS_TC_MIN_POINTS dispatches to the tcgen05 kernels: loss 1e-5, G 1e-5 and
+    gradients 2e-3 against the fp32 FFMA kernel on the same rollout (the gradient bound allows for the
+    ReLU-mask flips explained in the module docstring; without flips the two agree to 5e-6)."""
+    import soc_matching_b200 as sb
+    d, K, B = 10, 63, 1024
+    st = random_setting("double_well", d, seed=4)
+    hd, hm = [256, 128, 64], [128, 128]
+    unet, mnet = seeded_unet(d, hd, 5), seeded_mnet(d, hm, 6, 0.1)
+    gam = {"gamma": torch.tensor([6.0]), "gamma2": torch.tensor([1.0]), "gamma3": torch.tensor([1.0])}
+    noises = torch.randn(K, B, d, generator=torch.Generator().manual_seed(2)).to(DEV)
+    res = []
+    for ffma in (True, False):
+        sde = make_product_sde(st, unet, mnet, gam, hd, hm, DEV)
+        solver = sb.SOC_Solver(sde, torch.zeros(d, device=DEV), None, T=1.0, num_steps=K, lmbd=1.0, d=d,
+                               sigma=sde.sigma)
+        solver.force_ffma = ffma
+        solver.inject_noise(noises)
+        out = solver.loss(B, algorithm="SOCM")
+        out[0].backward()
+        res.append((float(out[0].detach()), {n: q.grad.clone() for n, q in sde.named_parameters() if q.grad is not None}))
+    (l0, g0), (l1, g1) = res
+    assert abs(l0 - l1) <= 1e-5 * abs(l0)
+    for n in g0:
+        assert rel_l2(g1[n], g0[n]) <= 2e-3, (n, rel_l2(g1[n], g0[n]))

@@ -1,6 +1,6 @@
 """K3b (csrc/wgrad_tc.cu) on a synthetic scratch: every weight / bias gradient of the default UNet
-equals sum_p dY[p] (x) Act[p] computed by torch (operands pre-rounded to tf32 so that the comparison
-isolates the layout / accumulation, tolerance 1e-5 relative)."""
+equals sum_p dY[p] (x) Act[p] computed by torch in fp64 from the same fp32 operands (3xTF32 in the
+kernel, fp32 accumulation over all points in TMEM: tolerance 1e-5 relative; a single TF32 pass gives ~3e-4)."""
 import numpy as np
 import pytest
 import torch
@@ -44,7 +44,7 @@ def test_wgrad_tc_matches_torch(d, n_tiles):
     assert lib.socm_debug_wgrad_tile_bytes() == 4 * NFB * 4096
     g = torch.Generator().manual_seed(d * 100 + n_tiles)
     P = n_tiles * 128
-    t = {k: tf32(torch.randn(P, w, generator=g)) for k, w in WIDTH.items()}
+    t = {k: torch.randn(P, w, generator=g) for k, w in WIDTH.items()}
     t["XIN"][:, d + 1:] = 0
     t["XIN"][:, 31] = 1.0
     t["DY0"][:, d:] = 0
