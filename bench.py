@@ -177,22 +177,37 @@ def gpu_arm(args):
 
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel (K3: fused UNet fwd + loss + dgrad + wgrad)
+    # ---- roofline of the dominant kernels (K3 = loss_tc_kernel + wgrad_tc_kernel: UNet forward + loss +
+    # dgrad + wgrad at every trajectory point).  achieved = algorithmic FLOP of one K3 call / its
+    # CUDA-event time; peak = measured dense bf16 GEMM (sustained, the kernel runs inside a long step).
+    # The kernels issue kind::tf32 MMAs three times per product (3xTF32, fp32-class accuracy), so the
+    # ceiling of this arithmetic is peak / 2 (tf32 rate) / 3 = peak / 6; both fractions are reported.
     chunk = min(hi - lo, solver.chunk_paths)
     k3_ms = kernel_ms.get("loss_fwdbwd", float("nan"))
     k3_flop = FLOP_K3_POINT * (K_STEPS + 1) * chunk
     achieved = k3_flop / (k3_ms * 1e-3) / 1e12
     tensor_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-    sm_mhz = clocks.get("sm_mhz") or 1965.0
-    ffma_peak = 2 * 128 * torch.cuda.get_device_properties(dev).multi_processor_count * sm_mhz * 1e6 / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_k3_traffic.json")
+    if os.path.exists(tpath):   # dram bytes of K3a + K3b from the committed ncu capture, per trajectory point
+        tj = json.load(open(tpath))
+        traffic = tj["dram_bytes_per_point"] * (K_STEPS + 1) * chunk
+    k1_ms = kernel_ms.get("rollout", float("nan"))
+    k1_tflops = FLOP_FWD * K_STEPS * chunk / (k1_ms * 1e-3) / 1e12
     roofline = {
-        "kernel": "loss_tile_kernel (K3)", "bound": "tensor", "achieved": round(achieved, 2),
-        "peak": tensor_peak, "unit": "TFLOP/s", "frac": round(achieved / tensor_peak, 4),
-        "traffic": None, "peak_source": f"{peak_src} bf16_tflops_sustained",
-        "note": "round-1 kernel is the fp32 FFMA parity path (no tensor cores yet); vs the FP32 pipe: "
-                f"{achieved / ffma_peak:.3f} of {ffma_peak:.1f} TFLOP/s nominal at the sampled SM clock",
+        "kernel": "K3: loss_tc_kernel + wgrad_tc_kernel (tcgen05, 3xTF32)", "bound": "tensor",
+        "achieved": round(achieved, 2), "peak": tensor_peak, "unit": "TFLOP/s", "frac": round(achieved / tensor_peak, 4),
+        "traffic": traffic, "peak_source": f"{peak_src} bf16_tflops_sustained",
+        "frac_of_3xtf32_ceiling": round(achieved / (tensor_peak / 6.0), 4),
+        "note": "algorithmic fp32 FLOP (each product costs 3 tf32 MMAs: ceiling = peak/6); "
+                "DRAM traffic is dominated by the wgrad operand scratch (DESIGN.md 3.4)",
         "algorithmic_flop_per_launch": k3_flop, "avg_launch_ms": round(k3_ms, 3),
         "kernel_share_of_step": round(k3_ms * kernel_n.get("loss_fwdbwd", 0) / args.steps / ms_per_step, 3),
+        "rollout": {"kernel": "rollout_tc_kernel (tcgen05, 3xTF32)", "achieved_tflops": round(k1_tflops, 2),
+                    "frac": round(k1_tflops / tensor_peak, 4),
+                    "frac_of_3xtf32_ceiling": round(k1_tflops / (tensor_peak / 6.0), 4),
+                    "hbm_gbs": round(chunk * K_STEPS * 128 / (k1_ms * 1e-3) / 1e9, 1),
+                    "hbm_frac": round(chunk * K_STEPS * 128 / (k1_ms * 1e-3) / 1e9 / float(peaks["hbm_gbs"]), 4)},
     }
     cpu = cpu_baseline(sample_batch=128, reps=1) if world == 1 and not args.no_cpu else None
     line = {
@@ -201,7 +216,7 @@ def gpu_arm(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "double_well d=10 num_steps=200 gamma=6 SOCM (rollout + target + loss + backward)",
                    "global_batch": B, "paths_per_gpu": hi - lo, "chunk_paths": chunk, "hdims": [256, 128, 64],
-                   "hdims_M": [128, 128], "noise": "in-kernel Philox4x32-10",
+                   "hdims_M": [128, 128], "noise": "in-kernel Philox4x32-10", "arithmetic": "fp32 (UNet GEMMs as 3xTF32 on tcgen05)",
                    "l2": "working set per step (GBs of trajectories) is far larger than the 126 MB L2"},
         "socm_iters_per_s": 1e3 / ms_per_step,
         "kernel_ms_avg_per_launch": {k: round(v, 3) for k, v in kernel_ms.items()},

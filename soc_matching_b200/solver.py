@@ -101,6 +101,19 @@ class SOC_Solver(nn.Module):
         self.kernel_events.setdefault(name, []).append((a, b))
         return _lib.check(rc)
 
+    def _k3_launches(self, udesc, nb, K):
+        """Kernels one socm_unet_loss_fwdbwd_f32 call launches (csrc/loss.cu, loss_tc.cu): the tcgen05 path
+        packs the weight tapes once and runs K3a + K3b per sub-chunk of 8192 tiles; the FFMA tile path is
+        pack + kernel + gradient reduction; the generic path one kernel."""
+        default_arch = (udesc.h0, udesc.h1, udesc.h2) == (256, 128, 64)
+        if self.force_generic or not default_arch:
+            return 1
+        tc = (not self.force_ffma) and udesc.d <= 23 and (self.force_tc or (K + 1) * nb >= 65536)
+        if not tc:
+            return 3
+        n_tiles = (K + 1) * ((nb + 127) // 128)
+        return 1 + 2 * ((n_tiles + 8191) // 8192)
+
     def _grid(self):
         if self._pair_grid is None or self._pair_grid.t.device != self.ts.device:
             self._pair_grid = mtable.make_pair_grid(self.ts, self.T)
@@ -201,7 +214,7 @@ class SOC_Solver(nn.Module):
             else:
                 target_graph = self._stopping_target(sde, wsp, R, ts, K, d, nb)
                 target[:, :nrows].copy_(target_graph.detach())
-            self._timed("loss_fwdbwd", 3, lib.socm_unet_loss_fwdbwd_f32,
+            self._timed("loss_fwdbwd", self._k3_launches(udesc, nb, K), lib.socm_unet_loss_fwdbwd_f32,
                         desc.c_struct, udesc, warm_struct, _lib.ptr(ts_f32), _lib.ptr(wsp.states),
                         _lib.ptr(target), ldt, _lib.ptr(wbuf), _lib.ptr(wsp.stop) if stopping else None, scale, nb, K,
                         _lib.ptr(G), _lib.ptr(grad_flat), _lib.ptr(loss_sum), _lib.ptr(loss_ws),
