@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 D, K_STEPS, GAMMA = 10, 200, 6.0
 FLOP_FWD = 338652.0                       # one UNet evaluation at d=10
 FLOP_K3_POINT = 338652.0 + 338652.0 + 332800.0   # forward + wgrad + dgrad (no dgrad into [t,x])
+TF32_MEASURED = 1034.0                    # TFLOP/s, all 148 SMs issuing 128x256x8 kind::tf32 MMAs (profiles/r1_umma_probe.log)
 
 
 def load_peaks():
@@ -175,7 +176,11 @@ def gpu_arm(args):
         t_e2e = float(tt)
     e2e_value = B * K_STEPS / (t_e2e / e2e_steps)
 
+    if world > 1:
+        torch.distributed.barrier()
     if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
         return
     # ---- roofline of the dominant kernels (K3 = loss_tc_kernel + wgrad_tc_kernel: UNet forward + loss +
     # dgrad + wgrad at every trajectory point).  achieved = algorithmic FLOP of one K3 call / its
@@ -198,14 +203,15 @@ def gpu_arm(args):
         "kernel": "K3: loss_tc_kernel + wgrad_tc_kernel (tcgen05, 3xTF32)", "bound": "tensor",
         "achieved": round(achieved, 2), "peak": tensor_peak, "unit": "TFLOP/s", "frac": round(achieved / tensor_peak, 4),
         "traffic": traffic, "peak_source": f"{peak_src} bf16_tflops_sustained",
-        "frac_of_3xtf32_ceiling": round(achieved / (tensor_peak / 6.0), 4),
-        "note": "algorithmic fp32 FLOP (each product costs 3 tf32 MMAs: ceiling = peak/6); "
-                "DRAM traffic is dominated by the wgrad operand scratch (DESIGN.md 3.4)",
+        "frac_of_3xtf32_ceiling": round(achieved / (TF32_MEASURED / 3.0), 4),
+        "note": "algorithmic fp32 FLOP; every product is issued as 3 kind::tf32 MMAs, so the ceiling of this "
+                f"arithmetic is the measured dense tf32 rate ({TF32_MEASURED:.0f} TFLOP/s, scripts/umma_probe.cu, "
+                "profiles/r1_umma_probe.log) / 3; DRAM traffic is dominated by the wgrad operand scratch (DESIGN.md 3.4)",
         "algorithmic_flop_per_launch": k3_flop, "avg_launch_ms": round(k3_ms, 3),
         "kernel_share_of_step": round(k3_ms * kernel_n.get("loss_fwdbwd", 0) / args.steps / ms_per_step, 3),
         "rollout": {"kernel": "rollout_tc_kernel (tcgen05, 3xTF32)", "achieved_tflops": round(k1_tflops, 2),
                     "frac": round(k1_tflops / tensor_peak, 4),
-                    "frac_of_3xtf32_ceiling": round(k1_tflops / (tensor_peak / 6.0), 4),
+                    "frac_of_3xtf32_ceiling": round(k1_tflops / (TF32_MEASURED / 3.0), 4),
                     "hbm_gbs": round(chunk * K_STEPS * 128 / (k1_ms * 1e-3) / 1e9, 1),
                     "hbm_frac": round(chunk * K_STEPS * 128 / (k1_ms * 1e-3) / 1e9 / float(peaks["hbm_gbs"]), 4)},
     }
@@ -227,6 +233,8 @@ def gpu_arm(args):
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 def cpu_baseline(sample_batch=128, reps=1):

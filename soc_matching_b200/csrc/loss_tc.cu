@@ -29,6 +29,19 @@ namespace tc {
 
 using namespace umma;
 
+#ifdef SOCM_TC_PROF
+__device__ unsigned long long g_k3_prof[192];   // [E owner | E helper | M] x 64 phase slots (block 0), debug builds only
+#define K3P_DECL long long prof_t = clock64(); unsigned long long prof_acc[64] = {0}; int prof_i = 0
+#define K3P_RESET prof_i = 0
+#define K3P_MARK do { const long long t_ = clock64(); prof_acc[prof_i++ & 63] += (unsigned long long)(t_ - prof_t); prof_t = t_; } while (0)
+#define K3P_FLUSH(base, cond) do { if (blockIdx.x == 0 && (cond)) for (int i_ = 0; i_ < 64; ++i_) g_k3_prof[(base) + i_] = prof_acc[i_]; } while (0)
+#else
+#define K3P_DECL
+#define K3P_RESET
+#define K3P_MARK
+#define K3P_FLUSH(base, cond)
+#endif
+
 namespace k3 {
 constexpr int SM_RING = 0;
 constexpr int SM_CHUNK = SM_RING + NSTAGE * SLOT_BYTES;
@@ -52,19 +65,29 @@ __host__ __device__ inline int loss_tc_smem_bytes(int d) {
   return k3::SM_SMALL + small_tc(d).total * 4 + k3::N_BARS * 8 + 16;
 }
 
-// 16 consecutive features [f0, f0+16) (f0 = 0 or 16) of point-row r into feature block `blk` (plain fp32)
-__device__ __forceinline__ void store_fb16(unsigned char* blk, int r, int f0, const float* v) {
-  unsigned char* row = blk + r * 128;
+// Scratch stores (layout of loss_tc.cuh): thread <-> point r of the quarter; `ro` = the eight
+// lane-dependent chunk offsets ((r >> 2) ^ k) * 16 + (r & 3) * 4, k = f & 7, precomputed once.
+struct RowOff {
+  int o[8];
+  __device__ __forceinline__ explicit RowOff(int r) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int f = f0 + 4 * q;
-    *reinterpret_cast<float4*>(row + (((f >> 3) ^ (r & 3)) << 5) + (f & 7) * 4) =
-        make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    for (int k = 0; k < 8; ++k) o[k] = ((((r >> 2) ^ k) & 7) << 4) + (r & 3) * 4;
   }
+};
+// features [f0, f0+16) of feature block `blk` (one coalesced 128-byte line per warp-wide store)
+__device__ __forceinline__ void store_fb16(unsigned char* blk, const RowOff& ro, int f0, const float* v) {
+#ifdef SOCM_K3_NOSTORE
+  return;
+#endif
+#pragma unroll
+  for (int j = 0; j < 16; ++j) *reinterpret_cast<float*>(blk + (f0 + j) * 128 + ro.o[(f0 + j) & 7]) = v[j];
 }
-__device__ __forceinline__ void store_fb32(unsigned char* blk, int r, const float* v) {
-  store_fb16(blk, r, 0, v);
-  store_fb16(blk, r, 16, v + 16);
+__device__ __forceinline__ void store_fb32(unsigned char* blk, const RowOff& ro, const float* v) {
+#ifdef SOCM_K3_NOSTORE
+  return;
+#endif
+#pragma unroll
+  for (int j = 0; j < 32; ++j) *reinterpret_cast<float*>(blk + j * 128 + ro.o[j & 7]) = v[j];
 }
 template <int NV>
 __device__ __forceinline__ uint32_t positive_bits(const float* v) {
@@ -139,6 +162,7 @@ __global__ void __launch_bounds__(k3::NT, 1)
     auto e_program = [&](auto h_const) {
       constexpr int h = decltype(h_const)::value;  // column half; h == 0 threads own the point
       const int p = tid & (TP - 1), r = tid & 31, q = (tid >> 5) & 3;
+      const RowOff ro(r);
       const uint32_t lane_t = tm + ((uint32_t)(q * 32) << 16);
       uint32_t g = 0;   // tiles done
       uint32_t cu = 0;  // chunks produced
@@ -146,6 +170,7 @@ __global__ void __launch_bounds__(k3::NT, 1)
       float* xin_lo = reinterpret_cast<float*>(smem + SM_XIN + KIN * 512);
       float* stage_f = reinterpret_cast<float*>(smem + SM_CHUNK);
       double loss_acc = 0.0;
+      K3P_DECL;
 
       for (int lt = blockIdx.x; lt < n_tiles_launch; lt += gridDim.x, ++g) {
         const int t = tile0 + lt;
@@ -156,6 +181,8 @@ __global__ void __launch_bounds__(k3::NT, 1)
         unsigned char* sq = scratch + (size_t)lt * TILE_BYTES + (size_t)q * QUARTER_BYTES;  // this warp's quarter
         uint32_t m_r1[8], m_r2[2], m_r3 = 0, m_y2[2], m_y1[8];
         float x[KIN];
+        K3P_RESET;
+        K3P_MARK;
 
         // chunk producer: v(16 cols) = f(D0 columns) -> shared-memory A chunk; `fn` post-processes the 16 values
         auto chunks = [&](auto&& fn) {
@@ -179,13 +206,10 @@ __global__ void __launch_bounds__(k3::NT, 1)
 #pragma unroll
           for (int j = 0; j < KIN; ++j)
             x[j] = (j < d && live) ? __ldg(a.states + ((size_t)ti * B + m) * d + j) : 0.f;
-          float xb[32];
-#pragma unroll
-          for (int c = 0; c < 32; ++c) xb[c] = 0.f;
+          float xb[KIN];
           xb[0] = tk;
 #pragma unroll
           for (int c = 1; c < KIN; ++c) xb[c] = x[c - 1];
-          xb[ONES_FEATURE] = 1.0f;
 #pragma unroll
           for (int c4 = 0; c4 < KIN / 4; ++c4) {
             float4 hh, ll;
@@ -197,18 +221,28 @@ __global__ void __launch_bounds__(k3::NT, 1)
           }
           fence_async_smem();
           warp_arrive(&bars[XIN_FULL]);
-          store_fb32(sq + FB_XIN * FB_BYTES, r, xb);
+          // XIN block of the scratch: features [t, x, 0.., 1 at ONES_FEATURE]
+          unsigned char* xblk = sq + FB_XIN * FB_BYTES;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float val = c < KIN ? xb[c < KIN ? c : 0] : (c == ONES_FEATURE ? 1.0f : 0.f);
+            *reinterpret_cast<float*>(xblk + c * 128 + ro.o[c & 7]) = val;
+          }
         }
         // ---- F1: r1 chunks for down_1 (+ mask, + scratch)
+        K3P_MARK;
         mbar_wait(&bars[D0_FULL], ph);
+        K3P_MARK;
         fence_after_sync();
         chunks([&](int c, float* v) {
           bias_relu16(v, sm_small + so.b_d0 + 32 * c + 16 * h);
           m_r1[c] = positive_bits<16>(v);
-          store_fb16(sq + (FB_R1 + c) * FB_BYTES, r, 16 * h, v);
+          store_fb16(sq + (FB_R1 + c) * FB_BYTES, ro, 16 * h, v);
         });
         // ---- F2: r2
+        K3P_MARK;
         mbar_wait(&bars[D1_FULL], ph);
+        K3P_MARK;
         fence_after_sync();
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -219,13 +253,15 @@ __global__ void __launch_bounds__(k3::NT, 1)
           bias_relu32(v, sm_small + so.b_d1 + 32 * cb);
           m_r2[i] = positive_bits<32>(v);
           store_split32(lane_t + C_SA + 32 * cb, lane_t + C_SA + 128 + 32 * cb, v);
-          store_fb32(sq + (FB_R2 + cb) * FB_BYTES, r, v);
+          store_fb32(sq + (FB_R2 + cb) * FB_BYTES, ro, v);
         }
         tmem_wait_st();
         fence_before_sync();
         warp_arrive(&bars[R2_FULL]);
         // ---- F3: r3
+        K3P_MARK;
         mbar_wait(&bars[D2_FULL], ph);
+        K3P_MARK;
         fence_after_sync();
         {
           float v[32];
@@ -234,13 +270,15 @@ __global__ void __launch_bounds__(k3::NT, 1)
           bias_relu32(v, sm_small + so.b_d2 + 32 * h);
           m_r3 = positive_bits<32>(v);
           store_split32(lane_t + C_R3 + 32 * h, lane_t + C_R3 + 64 + 32 * h, v);
-          store_fb32(sq + (FB_R3 + h) * FB_BYTES, r, v);
+          store_fb32(sq + (FB_R3 + h) * FB_BYTES, ro, v);
         }
         tmem_wait_st();
         fence_before_sync();
         warp_arrive(&bars[R3_FULL]);
         // ---- F4: y2 = relu(D3 + b_u2) in place
+        K3P_MARK;
         mbar_wait(&bars[D3A_FULL], ph);
+        K3P_MARK;
         fence_after_sync();
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -256,7 +294,9 @@ __global__ void __launch_bounds__(k3::NT, 1)
         fence_before_sync();
         warp_arrive(&bars[Y2_FULL]);
         // ---- F5: o2
+        K3P_MARK;
         mbar_wait(&bars[D3B_FULL], ph);
+        K3P_MARK;
         fence_after_sync();
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -266,13 +306,15 @@ __global__ void __launch_bounds__(k3::NT, 1)
           tmem_wait_ld();
           bias32(v, sm_small + so.b_r2 + 32 * cb);
           store_split32(lane_t + C_SA + 32 * cb, lane_t + C_SA + 128 + 32 * cb, v);
-          store_fb32(sq + (FB_O2 + cb) * FB_BYTES, r, v);
+          store_fb32(sq + (FB_O2 + cb) * FB_BYTES, ro, v);
         }
         tmem_wait_st();
         fence_before_sync();
         warp_arrive(&bars[O2_FULL]);
         // ---- F6: y1 = relu(D4 + b_u1) in place, chunk-style column ownership (16 columns of every 32)
+        K3P_MARK;
         mbar_wait(&bars[D4A_FULL], ph);
+        K3P_MARK;
         fence_after_sync();
 #pragma unroll 1
         for (int c = 0; c < 8; ++c) {
@@ -287,11 +329,15 @@ __global__ void __launch_bounds__(k3::NT, 1)
         fence_before_sync();
         warp_arrive(&bars[Y1_FULL]);
         // ---- F7: r1 chunks again for res_1
+        K3P_MARK;
         mbar_wait(&bars[D0B_FULL], ph);
+        K3P_MARK;
         fence_after_sync();
         chunks([&](int c, float* v) { bias_relu16(v, sm_small + so.b_d0 + 32 * c + 16 * h); });
         // ---- F8: o1 = D4 + b_r1 (scratch), partial up_0 over this thread's columns
+        K3P_MARK;
         mbar_wait(&bars[D4B_FULL], ph);
+        K3P_MARK;
         fence_after_sync();
         float au[KIN];
 #pragma unroll
@@ -315,14 +361,16 @@ __global__ void __launch_bounds__(k3::NT, 1)
               au[4 * qq + 3] = fmaf(w.w, v[j], au[4 * qq + 3]);
             }
           }
-          store_fb16(sq + (FB_O1 + c) * FB_BYTES, r, 16 * h, v);
+          store_fb16(sq + (FB_O1 + c) * FB_BYTES, ro, 16 * h, v);
         }
         fence_before_sync();
         if (h == 1) {
 #pragma unroll
           for (int j = 0; j < KIN; ++j) stage_f[j * TP + p] = au[j];
         }
+        K3P_MARK;
         e_sync();
+        K3P_MARK;
         // ---- loss (owners): nabla_V, d loss / d nabla_V, G; d_y0 operand for the backward pass
         if (h == 0) {
           float gv[KIN], y0[KIN], dv[KIN];
@@ -367,16 +415,20 @@ __global__ void __launch_bounds__(k3::NT, 1)
                 if (j < d) dv[j] = dl[j];
             }
           }
-          float dy[32], dz[32];
+          float dy[KIN];
+          unsigned char* yblk = sq + FB_DY0 * FB_BYTES;
+          unsigned char* zblk = sq + FB_DO0 * FB_BYTES;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) dy[c] = dz[c] = 0.f;
-#pragma unroll
-          for (int j = 0; j < KIN; ++j) {
-            dz[j] = dv[j];                          // d_o0
-            dy[j] = y0[j] > 0.f ? dv[j] : 0.f;      // d_y0
+          for (int c = 0; c < 32; ++c) {
+            float vy = 0.f, vz = 0.f;
+            if (c < KIN) {
+              vz = dv[c < KIN ? c : 0];                               // d_o0
+              vy = y0[c < KIN ? c : 0] > 0.f ? vz : 0.f;              // d_y0
+              dy[c < KIN ? c : 0] = vy;
+            }
+            *reinterpret_cast<float*>(yblk + c * 128 + ro.o[c & 7]) = vy;
+            *reinterpret_cast<float*>(zblk + c * 128 + ro.o[c & 7]) = vz;
           }
-          store_fb32(sq + FB_DY0 * FB_BYTES, r, dy);
-          store_fb32(sq + FB_DO0 * FB_BYTES, r, dz);
 #pragma unroll
           for (int c4 = 0; c4 < KIN / 4; ++c4) {
             float4 hh, ll;
@@ -390,15 +442,19 @@ __global__ void __launch_bounds__(k3::NT, 1)
           warp_arrive(&bars[DY0_FULL]);
         }
         // ---- B1: d_y1 = m_y1 . d_o1 chunks (d_o1, d_y1 -> scratch)
+        K3P_MARK;
         mbar_wait(&bars[BD0_FULL], ph);
+        K3P_MARK;
         fence_after_sync();
         chunks([&](int c, float* v) {
-          store_fb16(sq + (FB_DO1 + c) * FB_BYTES, r, 16 * h, v);
+          store_fb16(sq + (FB_DO1 + c) * FB_BYTES, ro, 16 * h, v);
           apply_bits<16>(v, m_y1[c]);
-          store_fb16(sq + (FB_DY1 + c) * FB_BYTES, r, 16 * h, v);
+          store_fb16(sq + (FB_DY1 + c) * FB_BYTES, ro, 16 * h, v);
         });
         // ---- B2: d_o2 -> A operand; d_o2, d_y2 -> scratch
+        K3P_MARK;
         mbar_wait(&bars[BDO2_FULL], ph);
+        K3P_MARK;
         fence_after_sync();
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -407,15 +463,17 @@ __global__ void __launch_bounds__(k3::NT, 1)
           tmem_ld32(lane_t + C_DO2 + 32 * cb, reinterpret_cast<uint32_t*>(v));
           tmem_wait_ld();
           store_split32(lane_t + C_SA + 32 * cb, lane_t + C_SA + 128 + 32 * cb, v);
-          store_fb32(sq + (FB_DO2 + cb) * FB_BYTES, r, v);
+          store_fb32(sq + (FB_DO2 + cb) * FB_BYTES, ro, v);
           apply_bits<32>(v, m_y2[i]);
-          store_fb32(sq + (FB_DY2 + cb) * FB_BYTES, r, v);
+          store_fb32(sq + (FB_DY2 + cb) * FB_BYTES, ro, v);
         }
         tmem_wait_st();
         fence_before_sync();
         warp_arrive(&bars[BO2_FULL]);
         // ---- B3: d_y2 -> A operand (once res_2^T has finished reading d_o2)
+        K3P_MARK;
         mbar_wait(&bars[BR2A_FULL], ph);
+        K3P_MARK;
         fence_after_sync();
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -430,7 +488,9 @@ __global__ void __launch_bounds__(k3::NT, 1)
         fence_before_sync();
         warp_arrive(&bars[BY2_FULL]);
         // ---- B4: d_z3 = m_r3 . d_r3 -> A operand [0,64) hi, [64,128) lo
+        K3P_MARK;
         mbar_wait(&bars[BD3_FULL], ph);
+        K3P_MARK;
         fence_after_sync();
         {
           float v[32];
@@ -438,13 +498,15 @@ __global__ void __launch_bounds__(k3::NT, 1)
           tmem_wait_ld();
           apply_bits<32>(v, m_r3);
           store_split32(lane_t + C_SA + 32 * h, lane_t + C_SA + 64 + 32 * h, v);
-          store_fb32(sq + (FB_DZ3 + h) * FB_BYTES, r, v);
+          store_fb32(sq + (FB_DZ3 + h) * FB_BYTES, ro, v);
         }
         tmem_wait_st();
         fence_before_sync();
         warp_arrive(&bars[BZ3_FULL]);
         // ---- B5: d_z2 = m_r2 . d_r2 -> A operand
+        K3P_MARK;
         mbar_wait(&bars[BR2B_FULL], ph);
+        K3P_MARK;
         fence_after_sync();
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -454,17 +516,21 @@ __global__ void __launch_bounds__(k3::NT, 1)
           tmem_wait_ld();
           apply_bits<32>(v, m_r2[i]);
           store_split32(lane_t + C_SA + 32 * cb, lane_t + C_SA + 128 + 32 * cb, v);
-          store_fb32(sq + (FB_DZ2 + cb) * FB_BYTES, r, v);
+          store_fb32(sq + (FB_DZ2 + cb) * FB_BYTES, ro, v);
         }
         tmem_wait_st();
         fence_before_sync();
         warp_arrive(&bars[BZ2_FULL]);
         // ---- B6: d_o1 chunks (unmasked) for res_1^T
+        K3P_MARK;
         mbar_wait(&bars[BD0B_FULL], ph);
+        K3P_MARK;
         fence_after_sync();
         chunks([&](int, float*) {});
         // ---- B7: d_z1 = m_r1 . d_r1 -> scratch
+        K3P_MARK;
         mbar_wait(&bars[BD1B_FULL], ph);
+        K3P_MARK;
         fence_after_sync();
 #pragma unroll 1
         for (int c = 0; c < 8; ++c) {
@@ -472,11 +538,14 @@ __global__ void __launch_bounds__(k3::NT, 1)
           tmem_ld16(lane_t + C_DR1 + 32 * c + 16 * h, reinterpret_cast<uint32_t*>(v));
           tmem_wait_ld();
           apply_bits<16>(v, m_r1[c]);
-          store_fb16(sq + (FB_DZ1 + c) * FB_BYTES, r, 16 * h, v);
+          store_fb16(sq + (FB_DZ1 + c) * FB_BYTES, ro, 16 * h, v);
         }
         fence_before_sync();  // TMEM reads done before the next tile's MMAs (ordered through XIN_FULL / e_sync)
+        K3P_MARK;
         e_sync();
+        K3P_MARK;
       }
+      K3P_FLUSH(h * 64, (tid & 127) == 0);
       // ---- loss: warp-shuffle reduction, one fp64 atomic per owner warp
       if (h == 0) {
 #pragma unroll
@@ -673,6 +742,12 @@ constexpr int SUB_TILES_MAX = 8192;  // tiles per K3a/K3b launch pair (scratch =
 bool loss_tc_supported(const socm_unet* net) { return is_default_arch(net) && kin_of(net->d) <= MAX_KIN; }
 
 static int64_t tape_bytes(int d) { return ((tc_workspace_bytes(d, true) + 1023) / 1024) * 1024; }
+
+#ifdef SOCM_TC_PROF
+extern "C" int socm_debug_k3_prof(unsigned long long* out192) {
+  return (int)cudaMemcpyFromSymbol(out192, g_k3_prof, sizeof(g_k3_prof));
+}
+#endif
 
 int64_t loss_tc_workspace_bytes(int d, int B, int K) {
   const int64_t n_tiles = (int64_t)(K + 1) * ((B + TP - 1) / TP);

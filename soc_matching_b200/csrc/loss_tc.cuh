@@ -2,14 +2,15 @@
 // wgrad_tc.cu = K3b: weight gradients).
 //
 // K3a hands K3b every operand of the weight-gradient GEMMs  dW[out][in] = sum_p dY[p][out] Act[p][in]
-// through a global scratch in exactly the shared-memory layout tcgen05.mma wants for an MN-major
-// tf32 operand (the only layout the hardware accepts there is SWIZZLE_128B with 32-byte atoms,
-// decoded with scripts/umma_decode.cu):
+// through a global scratch in exactly the shared-memory layout tcgen05.mma wants for a K-major tf32
+// operand with the 128-byte swizzle (K = trajectory points):
 //   a "feature block" = 32 consecutive features of one tensor for 32 consecutive points (a TMEM lane
-//   quarter = one warp of K3a) = 32 rows of 128 bytes; row r holds the 32 features of point r with
-//   its four 32-byte units XOR-permuted by (r & 3).  Values are plain fp32; K3b splits them into
-//   hi/lo in shared memory and runs the GEMMs as 3xTF32 (a single-pass TF32 weight gradient was
-//   measured at 1e-4 relative error on a 303-point case: not enough margin).
+//   quarter = one warp of K3a) = 32 rows of 128 bytes; row f holds the 32 points of feature f, its
+//   eight 16-byte chunks XOR-permuted by (f & 7).  With thread <-> point, one warp-wide 4-byte store
+//   of a feature is exactly one 128-byte line (fully coalesced), and one cp.async.bulk per operand
+//   lands a run of feature blocks in shared memory ready for the MMA.  Values are plain fp32; K3b
+//   splits them into hi/lo in shared memory and runs the GEMMs as 3xTF32 (a single-pass TF32 weight
+//   gradient was measured at 1e-4 relative error on a 303-point case: not enough margin).
 //   tile (128 points) -> 4 quarters -> NFB feature blocks of 4 KB.
 #pragma once
 #include "common.cuh"
@@ -42,8 +43,8 @@ constexpr int64_t TILE_BYTES = 4LL * QUARTER_BYTES;  // 1 097 728
 constexpr int ONES_FEATURE = 31;                     // constant-1 feature of the FB_XIN block (bias gradients)
 constexpr int MAX_D_TC_LOSS = 30;
 
-// byte offset of feature f (0..31) of point-row r (0..31) inside a feature block
-__host__ __device__ inline int fb_off(int r, int f) { return r * 128 + (((f >> 3) ^ (r & 3)) << 5) + (f & 7) * 4; }
+// byte offset of (feature f, point r), both 0..31, inside a feature block
+__host__ __device__ inline int fb_off(int r, int f) { return f * 128 + ((((r >> 2) ^ (f & 7)) & 7) << 4) + (r & 3) * 4; }
 
 // flat gradient layout (= socm_unet layer order, w then b per layer; same as loss_tile.cu)
 struct GradOffTc {

@@ -2,9 +2,10 @@
 // trajectory points as the contraction index (3xTF32, fp32 accumulation in TMEM).
 //
 //   dW[out][in] += sum_p dY[p][out] * Act[p][in]
-// Operands come from the scratch written by K3a (loss_tc.cuh): both are MN-major (features
-// contiguous, points = K) so a tile quarter of an operand is a run of 4 KB feature blocks that one
-// cp.async.bulk lands in shared memory ready for the MMA.  A persistent CTA walks the list of
+// Operands come from the scratch written by K3a (loss_tc.cuh): both are K-major with the 128-byte
+// swizzle (points contiguous per feature), so a tile quarter of an operand is a run of 4 KB feature
+// blocks that one cp.async.bulk lands in shared memory ready for the MMA (one K step = 8 points = 32
+// bytes along the row).  A persistent CTA walks the list of
 // "layer blocks" (128 output rows x N columns); for each it accumulates over all of its tiles in
 // TMEM and flushes once with red.global.add -- the flush traffic is negligible and the kernel is
 // bound by streaming the operands from HBM (DESIGN.md, K3b roofline).
@@ -59,9 +60,10 @@ constexpr int WG_STAGE_BYTES = 2 * 53248;
 constexpr int WG_A = 0, WG_B = 16384, WG_X = 49152;
 constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;  // + alignment slack + barriers
 constexpr int WG_NT = 192;
-constexpr uint64_t DESC_SW32B = 1ull << 61;  // layout type SWIZZLE_128B_BASE32B
+constexpr uint64_t DESC_SW128 = 2ull << 61;  // layout type SWIZZLE_128B
 
-__device__ __forceinline__ uint64_t mn_desc(uint32_t saddr) { return smem_desc(saddr, FB_BYTES, 512) | DESC_SW32B; }
+// K-major operand, 128-byte rows (32 points per feature), 8-row swizzle atoms of 1 KB stacked along the features
+__device__ __forceinline__ uint64_t mn_desc(uint32_t saddr) { return smem_desc(saddr, 16, 1024) | DESC_SW128; }
 
 __device__ __forceinline__ void red_add(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
@@ -130,8 +132,8 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
       if (my_tiles == 0) break;
       mbar_wait(acc_empty, (l & 1) ^ 1);  // the flush warps have drained the previous block
       fence_after_sync();
-      const uint32_t idesc = idesc_tf32(lb.M, lb.N, 1, 1);
-      const uint32_t idesc_x = idesc_tf32(lb.M, 32, 1, 1);
+      const uint32_t idesc = idesc_tf32(lb.M, lb.N, 0, 0);
+      const uint32_t idesc_x = idesc_tf32(lb.M, 32, 0, 0);
       uint32_t first = 1;
       for (int i = 0; i < my_tiles * 4; ++i, ++it) {
         const uint32_t s = it % WG_STAGES;
@@ -141,13 +143,13 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = mn_desc(st + WG_A + ks * 1024), al = mn_desc(st + WG_LO + WG_A + ks * 1024);
-            const uint64_t bd = mn_desc(st + WG_B + ks * 1024), bl = mn_desc(st + WG_LO + WG_B + ks * 1024);
+            const uint64_t ad = mn_desc(st + WG_A + ks * 32), al = mn_desc(st + WG_LO + WG_A + ks * 32);
+            const uint64_t bd = mn_desc(st + WG_B + ks * 32), bl = mn_desc(st + WG_LO + WG_B + ks * 32);
             mma_ss(tm, ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
             mma_ss(tm, al, bd, idesc, 1u);
             mma_ss(tm, ad, bl, idesc, 1u);
             if (lb.with_x) {
-              const uint64_t xd = mn_desc(st + WG_X + ks * 1024), xl = mn_desc(st + WG_LO + WG_X + ks * 1024);
+              const uint64_t xd = mn_desc(st + WG_X + ks * 32), xl = mn_desc(st + WG_LO + WG_X + ks * 32);
               mma_ss(tm + 256, ad, xd, idesc_x, (first && ks == 0) ? 0u : 1u);
               mma_ss(tm + 256, al, xd, idesc_x, 1u);
               mma_ss(tm + 256, ad, xl, idesc_x, 1u);

@@ -22,18 +22,18 @@ def tf32(x):
 
 
 def build_scratch(tensors, n_tiles):
-    """tensors[name]: (n_tiles*128, width) fp32 -> byte layout of loss_tc.cuh."""
-    words = torch.zeros(n_tiles, 4, NFB, 32, 32, dtype=torch.float32)       # tile, quarter, fb, row, word
-    r = torch.arange(32)
+    """tensors[name]: (n_tiles*128, width) fp32 -> byte layout of loss_tc.cuh: feature block = 32 feature
+    rows of 128 bytes (32 points), 16-byte chunks XOR-permuted by (feature & 7)."""
+    words = torch.zeros(n_tiles, 4, NFB, 32, 32, dtype=torch.float32)       # tile, quarter, fb, feature, word
+    f = torch.arange(32)
+    pt = torch.arange(32)
+    idx = (((pt[None, :] >> 2) ^ (f[:, None] & 7)) & 7) * 4 + (pt[None, :] & 3)   # (feature, point) -> word in the row
     for name, val in tensors.items():
         w = WIDTH[name]
-        v = val.reshape(n_tiles, 4, 32, w // 32, 4, 8)                      # tile, q, row, fb, unit, elem
-        for u in range(4):
-            phys = (u ^ (r & 3))                                            # per row
-            for fbi in range(w // 32):
-                blk = words[:, :, FB[name] + fbi]                           # tile, q, row, word
-                idx = (phys[:, None] * 8 + torch.arange(8)[None, :])        # row, elem -> word
-                blk.scatter_(3, idx[None, None].expand(n_tiles, 4, 32, 8), v[:, :, :, fbi, u, :])
+        v = val.reshape(n_tiles, 4, 32, w // 32, 32).permute(0, 1, 3, 4, 2)       # tile, q, fb, feature, point
+        blk = torch.zeros(n_tiles, 4, w // 32, 32, 32)
+        blk.scatter_(4, idx[None, None, None].expand(n_tiles, 4, w // 32, 32, 32), v)
+        words[:, :, FB[name]:FB[name] + w // 32] = blk
     return words.reshape(-1)
 
 
