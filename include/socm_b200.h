@@ -127,6 +127,11 @@ int socm_target_prep_f32(const socm_setting* st, const float* states, const floa
  * (zero for j < i: only K-blocks with j >= i are read). */
 int socm_target_gemm_f32(const float* L, const float* R, int32_t B, int32_t K, int32_t d,
                          int32_t ldr, float* target, int32_t ldt, void* stream);
+/* The same contraction on the tcgen05 tensor cores (3xTF32, fp32 accumulation; csrc/target_tc.cu).
+ * workspace: socm_target_gemm_tc_workspace_bytes(K, d) bytes (hi/lo split tape of L, rebuilt every call). */
+int64_t socm_target_gemm_tc_workspace_bytes(int32_t K, int32_t d);
+int socm_target_gemm_tc_f32(const float* L, const float* R, int32_t B, int32_t K, int32_t d, int32_t ldr,
+                            float* target, int32_t ldt, void* workspace, void* stream);
 /* dL[(K+1)d][ldr] (+)= G^T R  (contraction over paths), only the j >= i blocks are written. */
 int socm_target_gemm_bwd_f32(const float* G, const float* R, int32_t B, int32_t K, int32_t d,
                              int32_t ldr, int32_t ldt, float* dL, int32_t accumulate, void* stream);

@@ -181,6 +181,7 @@ class SOC_Solver(nn.Module):
         scale = 1.0 if stopping else 1.0 / ((K + 1) * B)                    # method.py:715 / 720
         warm_struct = simulate._warm_struct(warm_loss.A_loss, warm_loss.c_loss) if warm_loss is not None else None
         target_graph = None   # stopping case: the torch-side target (keeps the autograd graph)
+        k2_ws = None          # workspace of the tcgen05 target GEMM
         if stopping and B > chunk:
             raise NotImplementedError("stopping-time SOCM is not chunked yet: batch_size must be <= chunk_paths")
 
@@ -209,8 +210,15 @@ class SOC_Solver(nn.Module):
                 self._timed("target", 1, lib.socm_target_const_m_f32, _lib.ptr(R), nb, K, d, ldr, _lib.ptr(target),
                             ldt, stream)
             elif not stopping:
-                self._timed("target", 1, lib.socm_target_gemm_f32, _lib.ptr(L.detach()), _lib.ptr(R), nb, K, d, ldr,
-                            _lib.ptr(target), ldt, stream)
+                if self.force_ffma or self.force_generic:      # fp32 SIMT GEMM
+                    self._timed("target", 1, lib.socm_target_gemm_f32, _lib.ptr(L.detach()), _lib.ptr(R), nb, K, d,
+                                ldr, _lib.ptr(target), ldt, stream)
+                else:                                          # tcgen05, 3xTF32 (tape pack + GEMM)
+                    if k2_ws is None:
+                        k2_ws = torch.empty(int(lib.socm_target_gemm_tc_workspace_bytes(K, d)), device=dev,
+                                            dtype=torch.uint8)
+                    self._timed("target", 2, lib.socm_target_gemm_tc_f32, _lib.ptr(L.detach()), _lib.ptr(R), nb, K, d,
+                                ldr, _lib.ptr(target), ldt, k2_ws.data_ptr(), stream)
             else:
                 target_graph = self._stopping_target(sde, wsp, R, ts, K, d, nb)
                 target[:, :nrows].copy_(target_graph.detach())
