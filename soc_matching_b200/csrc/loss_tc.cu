@@ -80,14 +80,14 @@ __device__ __forceinline__ void store_fb16(unsigned char* blk, const RowOff& ro,
   return;
 #endif
 #pragma unroll
-  for (int j = 0; j < 16; ++j) *reinterpret_cast<float*>(blk + (f0 + j) * 128 + ro.o[(f0 + j) & 7]) = v[j];
+  for (int j = 0; j < 16; ++j) __stcs(reinterpret_cast<float*>(blk + (f0 + j) * 128 + ro.o[(f0 + j) & 7]), v[j]);
 }
 __device__ __forceinline__ void store_fb32(unsigned char* blk, const RowOff& ro, const float* v) {
 #ifdef SOCM_K3_NOSTORE
   return;
 #endif
 #pragma unroll
-  for (int j = 0; j < 32; ++j) *reinterpret_cast<float*>(blk + j * 128 + ro.o[j & 7]) = v[j];
+  for (int j = 0; j < 32; ++j) __stcs(reinterpret_cast<float*>(blk + j * 128 + ro.o[j & 7]), v[j]);
 }
 template <int NV>
 __device__ __forceinline__ uint32_t positive_bits(const float* v) {
