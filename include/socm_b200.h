@@ -135,6 +135,11 @@ int socm_target_gemm_tc_f32(const float* L, const float* R, int32_t B, int32_t K
 /* dL[(K+1)d][ldr] (+)= G^T R  (contraction over paths), only the j >= i blocks are written. */
 int socm_target_gemm_bwd_f32(const float* G, const float* R, int32_t B, int32_t K, int32_t d,
                              int32_t ldr, int32_t ldt, float* dL, int32_t accumulate, void* stream);
+/* The same on the tcgen05 tensor cores (3xTF32; csrc/target_bwd_tc.cu).  workspace:
+ * socm_target_gemm_bwd_tc_workspace_bytes(B, K, d) bytes (transposed operand scratch). */
+int64_t socm_target_gemm_bwd_tc_workspace_bytes(int32_t B, int32_t K, int32_t d);
+int socm_target_gemm_bwd_tc_f32(const float* G, const float* R, int32_t B, int32_t K, int32_t d, int32_t ldr,
+                                int32_t ldt, float* dL, int32_t accumulate, void* workspace, void* stream);
 /* SOCM_const_M (method.py:289-369): target_i = sum_{j>=i} a_j + grad_g, i.e. M = I, dM = 0. */
 int socm_target_const_m_f32(const float* R, int32_t B, int32_t K, int32_t d, int32_t ldr,
                             float* target, int32_t ldt, void* stream);

@@ -182,6 +182,7 @@ class SOC_Solver(nn.Module):
         warm_struct = simulate._warm_struct(warm_loss.A_loss, warm_loss.c_loss) if warm_loss is not None else None
         target_graph = None   # stopping case: the torch-side target (keeps the autograd graph)
         k2_ws = None          # workspace of the tcgen05 target GEMM
+        k2b_ws, k2b_nb = None, -1
         if stopping and B > chunk:
             raise NotImplementedError("stopping-time SOCM is not chunked yet: batch_size must be <= chunk_paths")
 
@@ -230,8 +231,16 @@ class SOC_Solver(nn.Module):
                         | (_lib.LOSS_FORCE_FFMA if self.force_ffma else 0)
                         | (_lib.LOSS_FORCE_TC if self.force_tc else 0), stream)
             if L is not None:
-                self._timed("target_bwd", 1, lib.socm_target_gemm_bwd_f32, _lib.ptr(G), _lib.ptr(R), nb, K, d, ldr,
-                            ldt, _lib.ptr(dL), 1, stream)
+                if self.force_ffma or self.force_generic:      # fp32 SIMT GEMM
+                    self._timed("target_bwd", 1, lib.socm_target_gemm_bwd_f32, _lib.ptr(G), _lib.ptr(R), nb, K, d, ldr,
+                                ldt, _lib.ptr(dL), 1, stream)
+                else:                                          # tcgen05, 3xTF32 (2 transposes + GEMM)
+                    if k2b_ws is None or k2b_nb != nb:
+                        k2b_ws = torch.empty(int(lib.socm_target_gemm_bwd_tc_workspace_bytes(nb, K, d)), device=dev,
+                                             dtype=torch.uint8)
+                        k2b_nb = nb
+                    self._timed("target_bwd", 3, lib.socm_target_gemm_bwd_tc_f32, _lib.ptr(G), _lib.ptr(R), nb, K, d,
+                                ldr, ldt, _lib.ptr(dL), 1, k2b_ws.data_ptr(), stream)
             stop_all.append(wsp.stop if B <= chunk else wsp.stop.clone())
         self._injected_noise = None
         del keep

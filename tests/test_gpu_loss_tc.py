@@ -168,3 +168,33 @@ def test_target_gemm_tc_matches_fp64(d, K, B):
     want = R.double() @ L.double().t()
     assert rel_l2(T[:, :nrows].cpu(), want.cpu()) <= 6e-6      # measured 3.5e-6 at K = 200 (segmented accumulation)
     assert rel_l2(T2[:, :nrows].cpu(), want.cpu()) <= 2e-6
+
+
+@pytest.mark.parametrize("d,K,B", [(10, 200, 300), (1, 150, 64), (20, 50, 129), (3, 7, 5), (10, 100, 2048)])
+def test_target_gemm_bwd_tc_matches_fp64(d, K, B):
+    """K2 backward on tcgen05 (csrc/target_bwd_tc.cu): dL += G^T R on the block-upper-triangular part,
+    against torch fp64 (3xTF32, segmented accumulation: 1e-5 relative) and the fp32 SIMT kernel."""
+    from soc_matching_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(DEV).manual_seed(K + B)
+    nrows, kdim = (K + 1) * d, (2 * K + 1) * d
+    ldr, ldt = (kdim + 3) // 4 * 4, (nrows + 3) // 4 * 4
+    G = torch.randn(B, ldt, device=DEV, generator=g)
+    R = torch.randn(B, ldr, device=DEV, generator=g)
+    base = torch.randn(nrows, ldr, device=DEV, generator=g)
+    i_of_row = torch.arange(nrows, device=DEV) // d
+    col = torch.arange(ldr, device=DEV)
+    keep = (col[None, :] >= 2 * i_of_row[:, None] * d) & (col[None, :] < kdim)
+    dL = base.clone()
+    ws = torch.empty(int(lib.socm_target_gemm_bwd_tc_workspace_bytes(B, K, d)), device=DEV, dtype=torch.uint8)
+    _lib.check(lib.socm_target_gemm_bwd_tc_f32(G.data_ptr(), R.data_ptr(), B, K, d, ldr, ldt, dL.data_ptr(), 1,
+                                               ws.data_ptr(), _lib.stream_ptr()))
+    dL2 = base.clone()
+    _lib.check(lib.socm_target_gemm_bwd_f32(G.data_ptr(), R.data_ptr(), B, K, d, ldr, ldt, dL2.data_ptr(), 1,
+                                            _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    want = G[:, :nrows].double().t() @ R.double()
+    want = torch.where(keep, want, torch.zeros_like(want))
+    assert torch.equal((dL - base)[~keep], torch.zeros_like(base)[~keep])          # structural zeros untouched
+    assert rel_l2((dL - base).cpu(), want.cpu()) <= 1e-5
+    assert rel_l2((dL2 - base).cpu(), want.cpu()) <= 1e-5
