@@ -59,7 +59,8 @@ constexpr int WG_LO = 53248;                         // offset of the "lo" copy 
 constexpr int WG_STAGE_BYTES = 2 * 53248;
 constexpr int WG_A = 0, WG_B = 16384, WG_X = 49152;
 constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;  // + alignment slack + barriers
-constexpr int WG_NT = 192;
+constexpr int WG_NT = 320;  // warps 0-3 split + flush, 4 MMA, 5 producer, 6-9 split
+constexpr int WG_PREFETCH = 6;  // stages of L2 prefetch lookahead
 constexpr uint64_t DESC_SW128 = 2ull << 61;  // layout type SWIZZLE_128B
 
 // K-major operand, 128-byte rows (32 points per feature), 8-row swizzle atoms of 1 KB stacked along the features
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
     for (int s = 0; s < WG_STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
-      mbar_init(&split[s], 4);
+      mbar_init(&split[s], 8);
     }
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, 4);
@@ -103,14 +104,45 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
 
   if (warp == 5) {
     // ===================================================== producer: one stage = (layer block, tile, quarter)
+    // Only two stages fit in shared memory (raw + lo copies), far too little to cover the HBM latency, so
+    // the producer runs an L2 prefetch (cp.async.bulk.prefetch.L2) WG_PREFETCH stages ahead of the copies.
     if (elect_one()) {
+      struct Cursor {
+        int l, ti, q;  // layer block, index into this CTA's tiles, quarter
+      };
+      auto advance = [&](Cursor& c) {
+        if (++c.q == 4) {
+          c.q = 0;
+          if (++c.ti == my_tiles) {
+            c.ti = 0;
+            ++c.l;
+          }
+        }
+      };
+      auto prefetch = [&](const Cursor& c) {
+        if (c.l >= N_LB) return;
+        const LayerBlock lb = c_lb[c.l];
+        const unsigned char* qb = scratch + (size_t)(blockIdx.x + c.ti * gridDim.x) * TILE_BYTES + (size_t)c.q * QUARTER_BYTES;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(qb + (size_t)lb.a_fb * FB_BYTES), "r"(lb.M * 128) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(qb + (size_t)lb.b_fb * FB_BYTES), "r"(lb.N * 128) : "memory");
+        if (lb.with_x)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(qb + (size_t)FB_XIN * FB_BYTES), "r"(FB_BYTES) : "memory");
+      };
+      Cursor ahead{0, 0, 0};
+      if (my_tiles > 0)
+        for (int i = 0; i < WG_PREFETCH; ++i) {
+          prefetch(ahead);
+          advance(ahead);
+        }
       uint32_t it = 0;
-      for (int l = 0; l < N_LB; ++l) {
+      for (int l = 0; l < N_LB && my_tiles > 0; ++l) {
         const LayerBlock lb = c_lb[l];
         const uint32_t a_bytes = (uint32_t)lb.M * 128u, b_bytes = (uint32_t)lb.N * 128u;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
           const unsigned char* tile = scratch + (size_t)t * TILE_BYTES;
           for (int q = 0; q < 4; ++q, ++it) {
+            prefetch(ahead);
+            advance(ahead);
             const uint32_t s = it % WG_STAGES;
             mbar_wait(&empty[s], ((it / WG_STAGES) & 1) ^ 1);
             unsigned char* st = smem + s * WG_STAGE_BYTES;
@@ -164,9 +196,11 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
       __syncwarp();
     }
   } else {
-    // ===================================================== flush: TMEM lane r <-> output row of the block
-    const uint32_t lane_t = tm + ((uint32_t)(warp * 32) << 16);
-    const int r = tid;  // 0..127
+    // ===================================================== split (8 warps) + flush (warps 0-3: TMEM lane r <-> output row)
+    const bool flusher = warp < 4;
+    const int sid = flusher ? tid : tid - 64;  // 0..255 among the split threads
+    const uint32_t lane_t = tm + ((uint32_t)((warp & 3) * 32) << 16);
+    const int r = tid & 127;
     uint32_t it = 0;
     for (int l = 0; l < N_LB; ++l) {
       const LayerBlock lb = c_lb[l];
@@ -179,7 +213,7 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
         float4* raw = reinterpret_cast<float4*>(smem + s * WG_STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(smem + s * WG_STAGE_BYTES + WG_LO);
         auto split_range = [&](int f4_begin, int n_f4) {
-          for (int j = tid; j < n_f4; j += 128) {
+          for (int j = sid; j < n_f4; j += 256) {
             const float4 x = raw[f4_begin + j];
             float4 hi, y;
             hi.x = tf32_rn(x.x); hi.y = tf32_rn(x.y); hi.z = tf32_rn(x.z); hi.w = tf32_rn(x.w);
@@ -195,6 +229,7 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&split[s]);
       }
+      if (!flusher) continue;
       mbar_wait(acc_full, l & 1);
       fence_after_sync();
       const bool row_ok = true;
