@@ -198,3 +198,35 @@ def test_target_gemm_bwd_tc_matches_fp64(d, K, B):
     assert torch.equal((dL - base)[~keep], torch.zeros_like(base)[~keep])          # structural zeros untouched
     assert rel_l2((dL - base).cpu(), want.cpu()) <= 1e-5
     assert rel_l2((dL2 - base).cpu(), want.cpu()) <= 1e-5
+
+
+@pytest.mark.parametrize("kind,d,K,B,dense,stopping", [("ou_linear", 10, 40, 257, True, False),
+                                                        ("ou_quadratic", 20, 20, 200, True, False),
+                                                        ("molecular_dynamics", 1, 150, 200, False, True)])
+def test_tc_k3_general_loss_paths_agree_with_ffma(kind, d, K, B, dense, stopping):
+    """Dense sigma (generic per-point loss inside K3a) and stopping-time masks (per-point stop indicator,
+    Z = sum of indicators) through the tcgen05 K3: loss 1e-5 and gradients 2e-3 against the fp32 FFMA
+    kernels on the same injected noise (gradient bound: ReLU-mask flips, see the module docstring)."""
+    import soc_matching_b200 as sb
+    st = random_setting(kind, d, seed=d + K, dense_sigma=dense)
+    hd, hm = [256, 128, 64], [64, 64]
+    unet = seeded_unet(d, hd, 41 + d, 0.5 if stopping else 1.0)
+    mnet = seeded_mnet(d, hm, 42 + d, 0.1, 3 if stopping else 2)
+    gam = {"gamma": torch.tensor([2.0]), "gamma2": torch.tensor([1.0]), "gamma3": torch.tensor([1.0])}
+    x0 = -torch.ones(d) if stopping else 0.3 * torch.ones(d)
+    noises = torch.randn(K, B, d, generator=torch.Generator().manual_seed(7)).to(DEV)
+    res = []
+    for tc_path in (False, True):
+        sde = make_product_sde(st, unet, mnet, gam, hd, hm, DEV, stopping=stopping)
+        solver = sb.SOC_Solver(sde, x0.to(DEV), None, T=1.0, num_steps=K, lmbd=st.lmbd, d=d, sigma=sde.sigma)
+        solver.force_ffma, solver.force_tc = (not tc_path), tc_path
+        solver.inject_noise(noises)
+        out = solver.loss(B, algorithm="SOCM", use_stopping_time=stopping)
+        out[0].backward()
+        res.append((float(out[0].detach()), {n: q.grad.clone() for n, q in sde.nabla_V.named_parameters()},
+                    out[7].clone()))
+    (l0, g0, s0), (l1, g1, s1) = res
+    assert torch.equal(s0, s1)                                   # stopping indicators (tcgen05 vs FFMA rollout)
+    assert abs(l0 - l1) <= 1e-5 * abs(l0), (l0, l1)
+    for n in g0:
+        assert rel_l2(g1[n], g0[n]) <= 2e-3, (n, rel_l2(g1[n], g0[n]))
