@@ -187,7 +187,7 @@ def gpu_arm(args):
     # CUDA-event time; peak = measured dense bf16 GEMM (sustained, the kernel runs inside a long step).
     # The kernels issue kind::tf32 MMAs three times per product (3xTF32, fp32-class accuracy), so the
     # ceiling of this arithmetic is peak / 2 (tf32 rate) / 3 = peak / 6; both fractions are reported.
-    chunk = min(hi - lo, solver.chunk_paths)
+    chunk = min(hi - lo, solver.chunk_paths or (1 << 16))
     k3_ms = kernel_ms.get("loss_fwdbwd", float("nan"))
     k3_flop = FLOP_K3_POINT * (K_STEPS + 1) * chunk
     achieved = k3_flop / (k3_ms * 1e-3) / 1e12

@@ -737,7 +737,9 @@ __global__ void __launch_bounds__(k3::NT, 1)
 }
 
 // ---------------------------------------------------------------- host side
-constexpr int SUB_TILES_MAX = 8192;  // tiles per K3a/K3b launch pair (scratch = 1.1 MB per tile)
+constexpr int SUB_TILES_CAP = 8192;  // upper bound of the tiles per K3a/K3b launch pair (scratch = 1.1 MB per tile)
+// whole waves of persistent CTAs per launch pair: the largest multiple of the SM count below the cap
+static int sub_tiles_max() { return (SUB_TILES_CAP / sm_count()) * sm_count(); }
 
 bool loss_tc_supported(const socm_unet* net) { return is_default_arch(net) && kin_of(net->d) <= MAX_KIN; }
 
@@ -751,7 +753,7 @@ extern "C" int socm_debug_k3_prof(unsigned long long* out192) {
 
 int64_t loss_tc_workspace_bytes(int d, int B, int K) {
   const int64_t n_tiles = (int64_t)(K + 1) * ((B + TP - 1) / TP);
-  const int64_t sub = n_tiles < SUB_TILES_MAX ? n_tiles : SUB_TILES_MAX;
+  const int64_t sub = n_tiles < SUB_TILES_CAP ? n_tiles : SUB_TILES_CAP;
   return tape_bytes(d) + sub * TILE_BYTES + 1024;
 }
 
@@ -767,8 +769,9 @@ int launch_loss_tc(const LossArgs& a, const socm_unet* net, float* grad, void* w
   const int n_mblk = (a.B + TP - 1) / TP;
   const int64_t n_tiles = (int64_t)(a.K + 1) * n_mblk;
   const int kin = kin_of(d);
-  for (int64_t t0 = 0; t0 < n_tiles; t0 += SUB_TILES_MAX) {
-    const int nt = (int)((n_tiles - t0) < SUB_TILES_MAX ? (n_tiles - t0) : SUB_TILES_MAX);
+  const int sub_max = sub_tiles_max();
+  for (int64_t t0 = 0; t0 < n_tiles; t0 += sub_max) {
+    const int nt = (int)((n_tiles - t0) < sub_max ? (n_tiles - t0) : sub_max);
     const int grid = nt < sm_count() ? nt : sm_count();
 #define SOCM_LAUNCH_K3(KIN)                                                                               \
   do {                                                                                                    \

@@ -59,7 +59,7 @@ class SOC_Solver(nn.Module):
         self.lmbd, self.d = lmbd, d
         self.y0 = nn.Parameter(torch.randn(1, device=x0.device))       # method.py:172 (unused by SOCM)
         self.sigma = neural_sde.sigma if sigma is None else sigma
-        self.chunk_paths = 1 << 16
+        self.chunk_paths = None             # paths per kernel launch; None -> 4 full waves of 128-path tiles
         self.force_generic = False          # tests: run the shape-generic kernels
         self.force_ffma = False             # tests: fp32 FFMA tile kernels instead of the tcgen05 kernels
         self.force_tc = False               # tests: tcgen05 K3 even for small batches
@@ -112,7 +112,11 @@ class SOC_Solver(nn.Module):
         if not tc:
             return 3
         n_tiles = (K + 1) * ((nb + 127) // 128)
-        return 1 + 2 * ((n_tiles + 8191) // 8192)
+        import ctypes
+        sms = ctypes.c_int(0)
+        _lib.check(_lib.load().socm_device_info(ctypes.byref(sms), None))
+        sub = (8192 // max(int(sms.value), 1)) * max(int(sms.value), 1)   # csrc/loss_tc.cu: sub_tiles_max()
+        return 1 + 2 * ((n_tiles + sub - 1) // sub)
 
     def _grid(self):
         if self._pair_grid is None or self._pair_grid.t.device != self.ts.device:
@@ -168,6 +172,12 @@ class SOC_Solver(nn.Module):
             L = mtable.build_L(m_all, dm_all, grid, ldr)
             dL = torch.zeros(nrows, ldr, **f32)
 
+        if self.chunk_paths is None:
+            # whole waves of persistent CTAs (one 128-path tile per SM and wave): no ragged last wave
+            import ctypes
+            sms = ctypes.c_int(0)
+            _lib.check(lib.socm_device_info(ctypes.byref(sms), None))
+            self.chunk_paths = 4 * 128 * max(int(sms.value), 1)
         chunk = min(B, int(self.chunk_paths))
         wsp = simulate.RolloutWorkspace(desc, unet, chunk, K, dev, True)
         R = torch.empty(chunk, ldr, **f32)
