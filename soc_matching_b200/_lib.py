@@ -65,7 +65,7 @@ PROTOTYPES = {
 }
 # test-only entry points (not part of include/socm_b200.h)
 DEBUG_PROTOTYPES = {
-    "socm_debug_wgrad_tc": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
+    "socm_debug_wgrad_tc": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
     "socm_debug_wgrad_tile_bytes": (_i64, []),
 }
 

@@ -13,9 +13,10 @@ bool rollout_tc_supported(const socm_unet* net);
 int64_t rollout_tc_workspace_bytes(int d);
 int launch_rollout_tc(const RolloutArgs& a, const socm_unet* net, void* workspace, cudaStream_t stream);
 // split (3xTF32 hi/lo) weight tape(s) + small fp32 block of unet_tc.cuh
-int pack_tc(const socm_unet* net, unsigned char* tape, float* small, bool with_bwd, cudaStream_t stream);
+int pack_tc(const socm_unet* net, unsigned char* tape, bool with_bwd, cudaStream_t stream);
 // tcgen05 K3: loss_tc.cu (forward + loss + dgrad) and wgrad_tc.cu (weight gradients)
-int launch_wgrad_tc(const unsigned char* scratch, int n_tiles, int d, float* grad, cudaStream_t stream);
+// `aux`: AUX_FLOATS accumulators of loss_tc.cuh (S = d_y0^T r1, sb = sum d_y0), zeroed by the caller
+int launch_wgrad_tc(const unsigned char* scratch, int n_tiles, int d, float* grad, float* aux, cudaStream_t stream);
 bool loss_tc_supported(const socm_unet* net);
 int64_t loss_tc_workspace_bytes(int d, int B, int K);
 }  // namespace tc

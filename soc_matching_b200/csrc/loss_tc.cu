@@ -13,7 +13,7 @@
 //               d_o1 = W_u0^T d_y0            (chunk source in TMEM, like down_0)
 //               d_o2 = W_u1^T (m_y1 . d_o1)   (A = 32-feature chunks in shared memory, like down_1)
 //               d_r2 = W_r2^T d_o2 + W_d2^T (m_r3 . W_u2^T (m_y2 . d_o2))
-//               d_r1 = W_d1^T (m_r2 . d_r2) + W_r1^T d_o1
+//               d_r1 = W_d1^T (m_r2 . d_r2) + Wc^T d_y0      (res_1 folded into up_0, unet_tc.cuh: K = d)
 //               d_z1 = m_r1 . d_r1
 // TMEM columns (backward): [0,256) d_o1 accumulator / A operands (hi|lo);  [256,384) d_o2 acc, later
 // [256,320) d_r3 acc;  [384,512) d_r2 acc;  [256,512) d_r1 acc.
@@ -51,14 +51,15 @@ enum Bar {
   W_FULL = 0, W_EMPTY = W_FULL + NSTAGE, CH_FULL = W_EMPTY + NSTAGE, CH_EMPTY = CH_FULL + 2,
   // forward, one completion per tile each
   XIN_FULL = CH_EMPTY + 2, D0_FULL, D1_FULL, R2_FULL, D2_FULL, R3_FULL, D3A_FULL, Y2_FULL, D3B_FULL, O2_FULL,
-  D4A_FULL, D0B_FULL, Y1_FULL, D4B_FULL,
+  D4A_FULL, Y0_FULL,
   // backward
   DY0_FULL, BD0_FULL, BDO2_FULL, BO2_FULL, BR2A_FULL, BY2_FULL, BD3_FULL, BZ3_FULL, BR2B_FULL, BZ2_FULL,
-  BD1A_FULL, BD0B_FULL, BD1B_FULL, N_BARS
+  BD1B_FULL, N_BARS
 };
 constexpr int NT = 320, NE = 256;
 constexpr uint32_t C_SA = 0, C_D1 = 256, C_D2 = 256, C_D3 = 256, C_R3 = 384, C_D4 = 256;
 constexpr uint32_t C_DO2 = 256, C_DR2 = 384, C_DR3 = 256, C_DR1 = 256;
+constexpr uint32_t C_Y0P = 384, C_Y0 = 0;  // folded last layer: Wc r1 (next to down_1) and W_u0 y1 (after up_1)
 }  // namespace k3
 
 __host__ __device__ inline int loss_tc_smem_bytes(int d) {
@@ -127,8 +128,11 @@ __global__ void __launch_bounds__(k3::NT, 1)
   const int my_tiles = (n_tiles_launch - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const bool simple_loss = a.st.sigma_is_identity && a.warmA == nullptr;
   constexpr int S0 = KIN > 16 ? 2 : 1;
-  constexpr int NSF = 40 + 2 * S0;  // forward weight stages per tile
-  constexpr int NSB = 40 + 2 * S0;  // backward weight stages per tile
+  constexpr int NY = KIN <= 16 ? 16 : 32;  // N of the folded up_0 MMAs
+  constexpr int NU0 = NY == 16 ? 1 : 2;    // up_0 slots
+  constexpr int BPS = 8 / NU0;             // up_0 K-chunks per slot
+  constexpr int NSF = S0 + 24 + NU0;       // forward weight stages per tile (= forward tape slots, in order)
+  constexpr int NSB = 2 * S0 + 24;         // backward weight stages per tile
   (void)K;
 
   for (int i = tid; i < so.total; i += NT) sm_small[i] = __ldg(small_g + i);
@@ -143,11 +147,11 @@ __global__ void __launch_bounds__(k3::NT, 1)
     }
     mbar_init(&bars[XIN_FULL], TP / 32);
     mbar_init(&bars[DY0_FULL], TP / 32);
-    const int e2m[] = {R2_FULL, R3_FULL, Y2_FULL, O2_FULL, Y1_FULL, BO2_FULL, BY2_FULL, BZ3_FULL, BZ2_FULL};
-    for (int i = 0; i < 9; ++i) mbar_init(&bars[e2m[i]], NE / 32);
-    const int m2e[] = {D0_FULL, D1_FULL, D2_FULL, D3A_FULL, D3B_FULL, D4A_FULL, D0B_FULL, D4B_FULL, BD0_FULL,
-                       BDO2_FULL, BR2A_FULL, BD3_FULL, BR2B_FULL, BD1A_FULL, BD0B_FULL, BD1B_FULL};
-    for (int i = 0; i < 16; ++i) mbar_init(&bars[m2e[i]], 1);
+    const int e2m[] = {R2_FULL, R3_FULL, Y2_FULL, O2_FULL, BO2_FULL, BY2_FULL, BZ3_FULL, BZ2_FULL};
+    for (int i = 0; i < 8; ++i) mbar_init(&bars[e2m[i]], NE / 32);
+    const int m2e[] = {D0_FULL, D1_FULL, D2_FULL, D3A_FULL, D3B_FULL, D4A_FULL, Y0_FULL, BD0_FULL,
+                       BDO2_FULL, BR2A_FULL, BD3_FULL, BR2B_FULL, BD1B_FULL};
+    for (int i = 0; i < 13; ++i) mbar_init(&bars[m2e[i]], 1);
     mbar_init_fence();
   }
   if (warp == 8) tmem_alloc(tmem_slot, 512);
@@ -168,7 +172,6 @@ __global__ void __launch_bounds__(k3::NT, 1)
       uint32_t cu = 0;  // chunks produced
       float* xin_hi = reinterpret_cast<float*>(smem + SM_XIN);
       float* xin_lo = reinterpret_cast<float*>(smem + SM_XIN + KIN * 512);
-      float* stage_f = reinterpret_cast<float*>(smem + SM_CHUNK);
       double loss_acc = 0.0;
       K3P_DECL;
 
@@ -184,13 +187,13 @@ __global__ void __launch_bounds__(k3::NT, 1)
         K3P_RESET;
         K3P_MARK;
 
-        // chunk producer: v(16 cols) = f(D0 columns) -> shared-memory A chunk; `fn` post-processes the 16 values
-        auto chunks = [&](auto&& fn) {
+        // chunk producer: v(16 cols) = f(accumulator columns) -> shared-memory A chunk; `fn` post-processes the 16 values
+        auto chunks = [&](uint32_t src_col, auto&& fn) {
           for (int c = 0; c < 8; ++c) {
             const int b = cu & 1;
             mbar_wait(&bars[CH_EMPTY + b], ((cu >> 1) & 1) ^ 1);
             float v[16];
-            tmem_ld16(lane_t + C_SA + 32 * c + 16 * h, reinterpret_cast<uint32_t*>(v));
+            tmem_ld16(lane_t + src_col + 32 * c + 16 * h, reinterpret_cast<uint32_t*>(v));
             tmem_wait_ld();
             fn(c, v);
             store_chunk16(smem + SM_CHUNK + b * CHUNK_BYTES, p, 4 * h, v);
@@ -234,7 +237,7 @@ __global__ void __launch_bounds__(k3::NT, 1)
         mbar_wait(&bars[D0_FULL], ph);
         K3P_MARK;
         fence_after_sync();
-        chunks([&](int c, float* v) {
+        chunks(C_SA, [&](int c, float* v) {
           bias_relu16(v, sm_small + so.b_d0 + 32 * c + 16 * h);
           m_r1[c] = positive_bits<16>(v);
           store_fb16(sq + (FB_R1 + c) * FB_BYTES, ro, 16 * h, v);
@@ -244,6 +247,15 @@ __global__ void __launch_bounds__(k3::NT, 1)
         mbar_wait(&bars[D1_FULL], ph);
         K3P_MARK;
         fence_after_sync();
+        float au[KIN];  // owners: (Wc r1)[j], later the whole pre-activation of up_0
+        if (h == 0) {
+          float yp[NY];
+          if constexpr (NY == 16) tmem_ld16(lane_t + C_Y0P, reinterpret_cast<uint32_t*>(yp));
+          else tmem_ld32(lane_t + C_Y0P, reinterpret_cast<uint32_t*>(yp));
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < KIN; ++j) au[j] = yp[j];
+        }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int cb = 2 * h + i;
@@ -311,65 +323,29 @@ __global__ void __launch_bounds__(k3::NT, 1)
         tmem_wait_st();
         fence_before_sync();
         warp_arrive(&bars[O2_FULL]);
-        // ---- F6: y1 = relu(D4 + b_u1) in place, chunk-style column ownership (16 columns of every 32)
+        // ---- F6: y1 = relu(D4 + b_u1) -> A chunks of the folded up_0 (+ mask, + scratch)
         K3P_MARK;
         mbar_wait(&bars[D4A_FULL], ph);
         K3P_MARK;
         fence_after_sync();
-#pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-          float v[16];
-          tmem_ld16(lane_t + C_D4 + 32 * c + 16 * h, reinterpret_cast<uint32_t*>(v));
-          tmem_wait_ld();
+        chunks(C_D4, [&](int c, float* v) {
           bias_relu16(v, sm_small + so.b_u1 + 32 * c + 16 * h);
           m_y1[c] = positive_bits<16>(v);
-          tmem_st16(lane_t + C_D4 + 32 * c + 16 * h, reinterpret_cast<const uint32_t*>(v));
-        }
-        tmem_wait_st();
-        fence_before_sync();
-        warp_arrive(&bars[Y1_FULL]);
-        // ---- F7: r1 chunks again for res_1
+          store_fb16(sq + (FB_Y1 + c) * FB_BYTES, ro, 16 * h, v);
+        });
+        // ---- F8 (owners): y0 = W_u0 y1 (TMEM [0,NY)) + Wc r1 (registers) + bc
         K3P_MARK;
-        mbar_wait(&bars[D0B_FULL], ph);
-        K3P_MARK;
-        fence_after_sync();
-        chunks([&](int c, float* v) { bias_relu16(v, sm_small + so.b_d0 + 32 * c + 16 * h); });
-        // ---- F8: o1 = D4 + b_r1 (scratch), partial up_0 over this thread's columns
-        K3P_MARK;
-        mbar_wait(&bars[D4B_FULL], ph);
-        K3P_MARK;
-        fence_after_sync();
-        float au[KIN];
-#pragma unroll
-        for (int j = 0; j < KIN; ++j) au[j] = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-          float v[16];
-          tmem_ld16(lane_t + C_D4 + 32 * c + 16 * h, reinterpret_cast<uint32_t*>(v));
+        if (h == 0) {
+          mbar_wait(&bars[Y0_FULL], ph);
+          fence_after_sync();
+          float yp[NY];
+          if constexpr (NY == 16) tmem_ld16(lane_t + C_Y0, reinterpret_cast<uint32_t*>(yp));
+          else tmem_ld32(lane_t + C_Y0, reinterpret_cast<uint32_t*>(yp));
           tmem_wait_ld();
-          const float* br = sm_small + so.b_r1 + 32 * c + 16 * h;
-          const float* wu = sm_small + so.u0t + (32 * c + 16 * h) * KIN;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            v[j] += br[j];
-#pragma unroll
-            for (int qq = 0; qq < KIN / 4; ++qq) {
-              const float4 w = *reinterpret_cast<const float4*>(wu + j * KIN + 4 * qq);
-              au[4 * qq] = fmaf(w.x, v[j], au[4 * qq]);
-              au[4 * qq + 1] = fmaf(w.y, v[j], au[4 * qq + 1]);
-              au[4 * qq + 2] = fmaf(w.z, v[j], au[4 * qq + 2]);
-              au[4 * qq + 3] = fmaf(w.w, v[j], au[4 * qq + 3]);
-            }
-          }
-          store_fb16(sq + (FB_O1 + c) * FB_BYTES, ro, 16 * h, v);
+          for (int j = 0; j < KIN; ++j) au[j] += yp[j];
+          fence_before_sync();  // TMEM reads before the backward MMAs into [0,256) (ordered through DY0_FULL)
         }
-        fence_before_sync();
-        if (h == 1) {
-#pragma unroll
-          for (int j = 0; j < KIN; ++j) stage_f[j * TP + p] = au[j];
-        }
-        K3P_MARK;
-        e_sync();
         K3P_MARK;
         // ---- loss (owners): nabla_V, d loss / d nabla_V, G; d_y0 operand for the backward pass
         if (h == 0) {
@@ -381,7 +357,7 @@ __global__ void __launch_bounds__(k3::NT, 1)
             float ar = fmaf(wr[0], tk, sm_small[so.b_r0 + j]);
 #pragma unroll
             for (int c = 1; c < KIN; ++c) ar = fmaf(wr[c], x[c - 1], ar);
-            y0[j] = au[j] + stage_f[j * TP + p] + sm_small[so.b_u0 + j];
+            y0[j] = au[j] + sm_small[so.bc + j];
             gv[j] = fmaxf(y0[j], 0.f) + ar;
             dv[j] = 0.f;
           }
@@ -446,8 +422,7 @@ __global__ void __launch_bounds__(k3::NT, 1)
         mbar_wait(&bars[BD0_FULL], ph);
         K3P_MARK;
         fence_after_sync();
-        chunks([&](int c, float* v) {
-          store_fb16(sq + (FB_DO1 + c) * FB_BYTES, ro, 16 * h, v);
+        chunks(C_SA, [&](int c, float* v) {
           apply_bits<16>(v, m_y1[c]);
           store_fb16(sq + (FB_DY1 + c) * FB_BYTES, ro, 16 * h, v);
         });
@@ -521,12 +496,6 @@ __global__ void __launch_bounds__(k3::NT, 1)
         tmem_wait_st();
         fence_before_sync();
         warp_arrive(&bars[BZ2_FULL]);
-        // ---- B6: d_o1 chunks (unmasked) for res_1^T
-        K3P_MARK;
-        mbar_wait(&bars[BD0B_FULL], ph);
-        K3P_MARK;
-        fence_after_sync();
-        chunks([&](int, float*) {});
         // ---- B7: d_z1 = m_r1 . d_r1 -> scratch
         K3P_MARK;
         mbar_wait(&bars[BD1B_FULL], ph);
@@ -577,24 +546,26 @@ __global__ void __launch_bounds__(k3::NT, 1)
       mbar_wait(&bars[bar], ph);
       fence_after_sync();
     };
-    auto small_k = [&]() {  // [0,256) = (SMEM operand [128 x KIN]) x (first tape block(s)): down_0 / up_0^T
+    // 256 columns at d_col (+)= (SMEM operand [128 x KIN]) x (S0 tape blocks): down_0 / up_0^T / Wc^T
+    auto small_k = [&](uint32_t d_col, bool fresh) {
 #pragma unroll
       for (int hh = 0; hh < S0; ++hh) {
         const uint32_t wb = wait_w();
-        if (elect_one()) issue_block_ss<H0 / S0, KIN>(tm + C_SA + hh * (H0 / S0), xin_s, KIN * 512, wb, true);
+        if (elect_one()) issue_block_ss<H0 / S0, KIN>(tm + d_col + hh * (H0 / S0), xin_s, KIN * 512, wb, fresh);
         __syncwarp();
         release_w();
       }
     };
     // A = 8 shared-memory chunks of 32 features; one block of K = 32 (N = 128) or two of K = 16 (N = 256) per chunk
-    auto chunk_layer_128 = [&](uint32_t d_col, bool fresh) {
+    auto chunk_layer_128 = [&](uint32_t d_col, bool with_wc) {  // with_wc: the slot also carries the Wc block (forward)
       for (int c = 0; c < 8; ++c) {
         const uint32_t b = cm & 1;
         mbar_wait(&bars[CH_FULL + b], (cm >> 1) & 1);
         fence_after_sync();
         const uint32_t wb = wait_w();
         if (elect_one()) {
-          issue_block_ss<H1, 32>(tm + d_col, chunk_s + b * CHUNK_BYTES, CHUNK_HALF, wb, fresh && c == 0);
+          issue_block_ss<H1, 32>(tm + d_col, chunk_s + b * CHUNK_BYTES, CHUNK_HALF, wb, c == 0);
+          if (with_wc) issue_block_ss<NY, 32>(tm + C_Y0P, chunk_s + b * CHUNK_BYTES, CHUNK_HALF, wb + MAIN_BYTES, c == 0);
           commit(&bars[CH_EMPTY + b]);
         }
         __syncwarp();
@@ -602,30 +573,30 @@ __global__ void __launch_bounds__(k3::NT, 1)
         ++cm;
       }
     };
-    auto chunk_layer_256 = [&](uint32_t d_col) {
-      for (int c = 0; c < 8; ++c) {
-        const uint32_t b = cm & 1;
-        mbar_wait(&bars[CH_FULL + b], (cm >> 1) & 1);
-        fence_after_sync();
-        for (int j = 0; j < 2; ++j) {
-          const uint32_t wb = wait_w();
+    auto up0_layer = [&]() {  // folded up_0: [0,NY) = y1 chunks x W_u0 blocks (8 K-chunks of 32, BPS per slot)
+      for (int u = 0; u < NU0; ++u) {
+        const uint32_t wb = wait_w();
+        for (int cc = 0; cc < BPS; ++cc) {
+          const uint32_t b = cm & 1;
+          mbar_wait(&bars[CH_FULL + b], (cm >> 1) & 1);
+          fence_after_sync();
           if (elect_one()) {
-            issue_block_ss<H0, 16>(tm + d_col, chunk_s + b * CHUNK_BYTES + j * 2 * ACT_KSTEP, CHUNK_HALF, wb, false);
-            if (j == 1) commit(&bars[CH_EMPTY + b]);
+            issue_block_ss<NY, 32>(tm + C_Y0, chunk_s + b * CHUNK_BYTES, CHUNK_HALF, wb + cc * (NY * 256), u == 0 && cc == 0);
+            commit(&bars[CH_EMPTY + b]);
           }
           __syncwarp();
-          release_w();
+          ++cm;
         }
-        ++cm;
+        release_w();
       }
     };
     for (uint32_t g = 0; g < (uint32_t)my_tiles; ++g) {
       const uint32_t ph = g & 1;
       // ================= forward
       wait_e(XIN_FULL, ph);
-      small_k();
+      small_k(C_SA, true);
       signal(D0_FULL);
-      chunk_layer_128(C_D1, true);  // down_1
+      chunk_layer_128(C_D1, true);  // down_1 (+ Wc r1)
       signal(D1_FULL);
       wait_e(R2_FULL, ph);          // down_2: A = r2 (TMEM)
       for (int j = 0; j < 2; ++j) {
@@ -659,17 +630,13 @@ __global__ void __launch_bounds__(k3::NT, 1)
         release_w();
       }
       signal(D4A_FULL);
-      wait_e(D4A_FULL, ph);         // up_1 has finished reading o2: down_0 again into [0,256)
-      small_k();
-      signal(D0B_FULL);
-      wait_e(Y1_FULL, ph);          // res_1 on top of relu(y1): A = r1 chunks
-      chunk_layer_256(C_D4);
-      signal(D4B_FULL);
+      up0_layer();                  // W_u0 y1 into [0,NY): the y1 chunks only exist once E has seen D4A_FULL
+      signal(Y0_FULL);
       // ================= backward
       wait_e(DY0_FULL, ph);         // d_o1 = d_y0 W_u0 into [0,256)
-      small_k();
+      small_k(C_SA, true);
       signal(BD0_FULL);
-      chunk_layer_128(C_DO2, true);  // d_o2 = d_y1 W_u1
+      chunk_layer_128(C_DO2, false);  // d_o2 = d_y1 W_u1
       signal(BDO2_FULL);
       wait_e(BO2_FULL, ph);          // d_r2 = d_o2 W_r2
       for (int j = 0; j < 4; ++j) {
@@ -702,11 +669,7 @@ __global__ void __launch_bounds__(k3::NT, 1)
         __syncwarp();
         release_w();
       }
-      signal(BD1A_FULL);
-      wait_e(BD1A_FULL, ph);         // d_z2 has been read: d_o1 again into [0,256)
-      small_k();
-      signal(BD0B_FULL);
-      chunk_layer_256(C_DR1);        // d_r1 += d_o1 W_r1
+      small_k(C_DR1, false);         // d_r1 += d_y0 Wc  (A = the d_y0 operand still in shared memory)
       signal(BD1B_FULL);
     }
   } else {
@@ -720,10 +683,9 @@ __global__ void __launch_bounds__(k3::NT, 1)
         const uint32_t s = i % NSTAGE;
         mbar_wait(&bars[W_EMPTY + s], ((i / NSTAGE) & 1) ^ 1);
         const bool bwd = in_tile >= (uint32_t)NSF;
-        const int st = bwd ? (int)in_tile - NSF : (int)in_tile;
-        const int slot_in = fwd_stage_slot(d, st);  // same consumption pattern on both tapes
+        const int slot_in = bwd ? (int)in_tile - NSF : (int)in_tile;
         const int slot = slot_in + (bwd ? n_fwd : 0);
-        const uint32_t bytes = slot_in < S0 ? (uint32_t)(2 * (H0 / S0) * KIN * 4) : (uint32_t)SLOT_BYTES;
+        const uint32_t bytes = bwd ? bwd_slot_bytes(d, slot_in) : fwd_slot_bytes(d, slot_in);
         mbar_expect_tx(&bars[W_FULL + s], bytes);
         bulk_g2s(smem + SM_RING + s * SLOT_BYTES, tape + (size_t)slot * SLOT_BYTES, bytes, &bars[W_FULL + s]);
         if (++in_tile == per_tile) in_tile = 0;
@@ -744,6 +706,31 @@ static int sub_tiles_max() { return (SUB_TILES_CAP / sm_count()) * sm_count(); }
 bool loss_tc_supported(const socm_unet* net) { return is_default_arch(net) && kin_of(net->d) <= MAX_KIN; }
 
 static int64_t tape_bytes(int d) { return ((tc_workspace_bytes(d, true) + 1023) / 1024) * 1024; }
+constexpr int64_t AUX_BYTES = ((AUX_FLOATS * 4 + 1023) / 1024) * 1024;
+
+// gradients of the folded pair (unet_tc.cuh) from S = d_y0^T r1 and sb = sum_p d_y0:
+//   dW_r1 += W_u0^T S,  db_r1 += W_u0^T sb,  dW_u0 += S W_r1^T + sb b_r1^T      (dW_u0 already holds d_y0^T y1)
+__global__ void fold_finish_kernel(socm_unet net, const float* __restrict__ aux, float* __restrict__ grad) {
+  const int d = net.d;
+  const GradOffTc go = grad_offsets_tc(d);
+  const float* S = aux + AUX_S;
+  const float* sb = aux + AUX_SB;
+  const int f = blockIdx.x, g = threadIdx.x;  // 256 x 256
+  float acc = 0.f;
+  for (int j = 0; j < d; ++j) acc = fmaf(net.w[8][(size_t)j * H0 + f], S[j * H0 + g], acc);
+  grad[go.w[4] + (size_t)f * H0 + g] += acc;
+  if (g == 0) {
+    float b = 0.f;
+    for (int j = 0; j < d; ++j) b = fmaf(net.w[8][(size_t)j * H0 + f], sb[j], b);
+    grad[go.b[4] + f] += b;
+  }
+  if (g < d) {  // dW_u0[j = g][f]
+    const int j = g;
+    float u = sb[j] * net.b[4][f];
+    for (int q = 0; q < H0; ++q) u = fmaf(S[j * H0 + q], net.w[4][(size_t)f * H0 + q], u);
+    grad[go.w[8] + (size_t)j * H0 + f] += u;
+  }
+}
 
 #ifdef SOCM_TC_PROF
 extern "C" int socm_debug_k3_prof(unsigned long long* out192) {
@@ -754,17 +741,19 @@ extern "C" int socm_debug_k3_prof(unsigned long long* out192) {
 int64_t loss_tc_workspace_bytes(int d, int B, int K) {
   const int64_t n_tiles = (int64_t)(K + 1) * ((B + TP - 1) / TP);
   const int64_t sub = n_tiles < SUB_TILES_CAP ? n_tiles : SUB_TILES_CAP;
-  return tape_bytes(d) + sub * TILE_BYTES + 1024;
+  return tape_bytes(d) + AUX_BYTES + sub * TILE_BYTES + 1024;
 }
 
 int launch_loss_tc(const LossArgs& a, const socm_unet* net, float* grad, void* workspace, cudaStream_t stream) {
   const int d = a.st.d;
   SOCM_CHECK_ARG(workspace != nullptr, "workspace is NULL (socm_loss_workspace_bytes)");
   unsigned char* tape = static_cast<unsigned char*>(workspace);
-  float* small = reinterpret_cast<float*>(tape + (size_t)2 * fwd_slots(d) * SLOT_BYTES);
-  unsigned char* scratch = tape + tape_bytes(d);
+  float* small = tc_small_ptr(tape, d, true);
+  float* aux = reinterpret_cast<float*>(tape + tape_bytes(d));
+  unsigned char* scratch = tape + tape_bytes(d) + AUX_BYTES;
   scratch += (1024 - (reinterpret_cast<uintptr_t>(scratch) & 1023)) & 1023;
-  if (int rc = pack_tc(net, tape, small, true, stream)) return rc;
+  if (int rc = pack_tc(net, tape, true, stream)) return rc;
+  SOCM_CUDA(cudaMemsetAsync(aux, 0, AUX_FLOATS * sizeof(float), stream));
   const int smem = loss_tc_smem_bytes(d);
   const int n_mblk = (a.B + TP - 1) / TP;
   const int64_t n_tiles = (int64_t)(a.K + 1) * n_mblk;
@@ -783,8 +772,10 @@ int launch_loss_tc(const LossArgs& a, const socm_unet* net, float* grad, void* w
     else SOCM_LAUNCH_K3(24);
 #undef SOCM_LAUNCH_K3
     SOCM_LAUNCH_CHECK();
-    if (int rc = launch_wgrad_tc(scratch, nt, d, grad, stream)) return rc;
+    if (int rc = launch_wgrad_tc(scratch, nt, d, grad, aux, stream)) return rc;
   }
+  fold_finish_kernel<<<H0, H0, 0, stream>>>(*net, aux, grad);
+  SOCM_LAUNCH_CHECK();
   return SOCM_OK;
 }
 

@@ -25,26 +25,30 @@ enum Fb {
   FB_R2 = 9,    // 4
   FB_R3 = 13,   // 2
   FB_O2 = 15,   // 4
-  FB_O1 = 19,   // 8
+  FB_Y1 = 19,   // 8   y1 = relu(up_1 o2): res_1 is folded into up_0 (unet_tc.cuh), o1 / d_o1 are never formed
   FB_DY0 = 27,  // d_y0 (features >= d are zero)
   FB_DO0 = 28,  // d_o0
   FB_DY1 = 29,  // 8
-  FB_DO1 = 37,  // 8
-  FB_DY2 = 45,  // 4
-  FB_DO2 = 49,  // 4
-  FB_DZ3 = 53,  // 2
-  FB_DZ2 = 55,  // 4
-  FB_DZ1 = 59,  // 8
-  NFB = 67
+  FB_DY2 = 37,  // 4
+  FB_DO2 = 41,  // 4
+  FB_DZ3 = 45,  // 2
+  FB_DZ2 = 47,  // 4
+  FB_DZ1 = 51,  // 8
+  NFB = 59
 };
 constexpr int FB_BYTES = 4096;
 constexpr int QUARTER_BYTES = NFB * FB_BYTES;
-constexpr int64_t TILE_BYTES = 4LL * QUARTER_BYTES;  // 1 097 728
+constexpr int64_t TILE_BYTES = 4LL * QUARTER_BYTES;  // 966 656
 constexpr int ONES_FEATURE = 31;                     // constant-1 feature of the FB_XIN block (bias gradients)
 constexpr int MAX_D_TC_LOSS = 30;
 
 // byte offset of (feature f, point r), both 0..31, inside a feature block
 __host__ __device__ inline int fb_off(int r, int f) { return f * 128 + ((((r >> 2) ^ (f & 7)) & 7) << 4) + (r & 3) * 4; }
+
+// K3b accumulates the two small products the folding needs into an aux block of the workspace
+//   S[j][g] = sum_p d_y0[p][j] r1[p][g]  (32 x 256, rows >= d zero)   and   sb[j] = sum_p d_y0[p][j]  (32)
+// and fold_finish_kernel (loss_tc.cu) turns them into the gradients of res_1 and the S-part of up_0.
+constexpr int AUX_S = 0, AUX_SB = 32 * 256, AUX_FLOATS = 32 * 256 + 32;
 
 // flat gradient layout (= socm_unet layer order, w then b per layer; same as loss_tile.cu)
 struct GradOffTc {

@@ -24,20 +24,39 @@ namespace tc {
 using namespace umma;
 
 // ---------------------------------------------------------------- weight repack (once per call)
-__global__ void pack_tc_kernel(socm_unet net, unsigned char* __restrict__ tape, float* __restrict__ small,
-                               int with_bwd) {
+// Wc = W_u0 W_r1 [d][256] (zero rows up to 32) and bc = W_u0 b_r1 + b_u0 (unet_tc.cuh, "folding"); fp64 accumulation
+__global__ void fold_tc_kernel(socm_unet net, float* __restrict__ wc, float* __restrict__ small) {
+  const int d = net.d, kin = kin_of(d);
+  const int j = blockIdx.x, g = threadIdx.x;  // 32 blocks x 256 threads
+  double acc = 0.0;
+  if (j < d)
+    for (int f = 0; f < H0; ++f) acc += (double)net.w[8][(size_t)j * H0 + f] * (double)net.w[4][(size_t)f * H0 + g];
+  wc[j * H0 + g] = (float)acc;
+  if (g == 0 && j < kin) {
+    double b = 0.0;
+    if (j < d) {
+      b = (double)net.b[8][j];
+      for (int f = 0; f < H0; ++f) b += (double)net.w[8][(size_t)j * H0 + f] * (double)net.b[4][f];
+    }
+    small[small_tc(d).bc + j] = (float)b;
+  }
+}
+
+__global__ void pack_tc_kernel(socm_unet net, const float* __restrict__ wc, unsigned char* __restrict__ tape,
+                               float* __restrict__ small, int with_bwd) {
   const int d = net.d, kin = kin_of(d);
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-  const int n_fwd = fwd_slots(d), n_slots = with_bwd ? 2 * n_fwd : n_fwd;
-  for (int s = 0; s < n_slots; ++s) {
-    const SlotDesc sd = s < n_fwd ? fwd_slot(d, s) : bwd_slot(d, s - n_fwd);
-    const float* W = net.w[sd.layer];
-    unsigned char* base = tape + (size_t)s * SLOT_BYTES;
+  const int n_fi = fwd_items(d), n_items = n_fi + (with_bwd ? bwd_items(d) : 0);
+  for (int it = 0; it < n_items; ++it) {
+    const PackItem pi = it < n_fi ? fwd_item(d, it) : bwd_item(d, it - n_fi);
+    const SlotDesc sd = pi.sd;
+    const float* W = sd.layer == WC_LAYER ? wc : net.w[sd.layer];
+    unsigned char* base = tape + (size_t)(pi.slot + (it < n_fi ? 0 : fwd_slots(d))) * SLOT_BYTES + pi.byte_off;
     const int slab = sd.N * sd.Kc * 4;
     for (int i = tid; i < sd.N * sd.Kc; i += nth) {
       const int n = i / sd.Kc, k = i - n * sd.Kc;
       float w = 0.f;
-      if (sd.k0 + k < sd.klim)
+      if (sd.k0 + k < sd.klim && sd.n0 + n < sd.nlim)
         w = sd.transposed ? W[(size_t)(sd.k0 + k) * sd.ktot + sd.n0 + n] : W[(size_t)(sd.n0 + n) * sd.ktot + sd.k0 + k];
       const float hi = tf32_rn(w);
       const int off = wslab_off(n, k, sd.Kc);
@@ -55,15 +74,7 @@ __global__ void pack_tc_kernel(socm_unet net, unsigned char* __restrict__ tape, 
   copy(so.b_u2, net.b[6], H1);
   copy(so.b_r2, net.b[5], H1);
   copy(so.b_u1, net.b[7], H0);
-  copy(so.b_r1, net.b[4], H0);
-  for (int i = tid; i < H0 * kin; i += nth) {
-    const int f = i / kin, j = i - f * kin;
-    small[so.u0t + i] = j < d ? net.w[8][(size_t)j * H0 + f] : 0.f;
-  }
-  for (int i = tid; i < kin; i += nth) {
-    small[so.b_u0 + i] = i < d ? net.b[8][i] : 0.f;
-    small[so.b_r0 + i] = i < d ? net.b[3][i] : 0.f;
-  }
+  for (int i = tid; i < kin; i += nth) small[so.b_r0 + i] = i < d ? net.b[3][i] : 0.f;
   for (int i = tid; i < kin * kin; i += nth) {
     const int j = i / kin, k = i - j * kin;
     small[so.r0 + i] = (j < d && k <= d) ? net.w[3][(size_t)j * (d + 1) + k] : 0.f;
@@ -78,7 +89,7 @@ constexpr int SM_SMALL = SM_XIN + MAX_KIN * 1024;  // xin: hi + lo, 128 x kin fl
 enum Bar {
   W_FULL = 0, W_EMPTY = W_FULL + NSTAGE, CH_FULL = W_EMPTY + NSTAGE, CH_EMPTY = CH_FULL + 2,
   XIN_FULL = CH_EMPTY + 2, D0_FULL, D1_FULL, R2_FULL, D2_FULL, R3_FULL, D3A_FULL, Y2_FULL, D3B_FULL, O2_FULL,
-  D4A_FULL, D0B_FULL, Y1_FULL, D4B_FULL, N_BARS
+  D4A_FULL, Y0_FULL, N_BARS
 };
 __host__ __device__ inline int rollout_tc_smem_bytes(int d) { return SM_SMALL + small_tc(d).total * 4 + N_BARS * 8 + 16; }
 
@@ -98,6 +109,9 @@ __device__ unsigned long long g_tc_prof[48];
 #endif
 // TMEM columns
 constexpr uint32_t C_SA = 0, C_D1 = 256, C_D2 = 256, C_D3 = 256, C_R3 = 384, C_D4 = 256;
+// folded last layer (unet_tc.cuh): C_Y0P = Wc r1, accumulated next to down_1 and read out before r3 is
+// written there; C_Y0 = W_u0 y1, accumulated over the y1 chunks once up_1 has consumed o2.
+constexpr uint32_t C_Y0P = 384, C_Y0 = 0;
 
 
 // eps[0..d) for (path m, step k) into registers: injected or Philox (same draws as draw_noise)
@@ -136,7 +150,10 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
   const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const bool diag = diag_fast_path(a.st, a.warmA != nullptr);
   constexpr int S0 = KIN > 16 ? 2 : 1;        // down_0 slots
-  constexpr int NS = 40 + 2 * S0;             // weight stages per step
+  constexpr int NY = KIN <= 16 ? 16 : 32;     // N of the folded up_0 MMAs
+  constexpr int NU0 = NY == 16 ? 1 : 2;       // up_0 slots
+  constexpr int BPS = 8 / NU0;                // up_0 K-chunks per slot
+  constexpr int NS = S0 + 24 + NU0;           // weight stages per step (= forward tape slots, in order)
 
   // ---- one-time setup
   for (int i = tid; i < so.total; i += NT_TC) sm_small[i] = __ldg(small_g + i);
@@ -150,10 +167,10 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
       mbar_init(&bars[CH_EMPTY + b], 1);
     }
     mbar_init(&bars[XIN_FULL], TP / 32);
-    const int e2m[] = {R2_FULL, R3_FULL, Y2_FULL, O2_FULL, Y1_FULL};
-    for (int i = 0; i < 5; ++i) mbar_init(&bars[e2m[i]], NE / 32);
-    const int m2e[] = {D0_FULL, D1_FULL, D2_FULL, D3A_FULL, D3B_FULL, D4A_FULL, D0B_FULL, D4B_FULL};
-    for (int i = 0; i < 8; ++i) mbar_init(&bars[m2e[i]], 1);
+    const int e2m[] = {R2_FULL, R3_FULL, Y2_FULL, O2_FULL};
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[e2m[i]], NE / 32);
+    const int m2e[] = {D0_FULL, D1_FULL, D2_FULL, D3A_FULL, D3B_FULL, D4A_FULL, Y0_FULL};
+    for (int i = 0; i < 7; ++i) mbar_init(&bars[m2e[i]], 1);
     mbar_init_fence();
   }
   if (warp == 8) tmem_alloc(tmem_slot, 512);
@@ -178,20 +195,21 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
     PROF_DECL;
     float* xin_hi = reinterpret_cast<float*>(smem + SM_XIN);
     float* xin_lo = reinterpret_cast<float*>(smem + SM_XIN + KIN * 512);
-    float* stage_f = reinterpret_cast<float*>(smem + SM_CHUNK);  // exchange area (chunk buffer 0, idle after res_1)
+    float* stage_f = reinterpret_cast<float*>(smem + SM_CHUNK);  // exchange area (chunk buffer 0, idle after up_0)
 
     float kap[KIN];  // kappa padded with zeros (diagonal fast path of the SDE step)
 #pragma unroll
     for (int j = 0; j < KIN; ++j) kap[j] = (h == 0 && diag && j < d) ? __ldg(a.st.kappa + j) : 0.f;
 
-    auto gen_chunks = [&]() {  // r1 = relu(D0 + b_d0) -> 8 shared-memory A chunks, 16 features per half
+    // relu(acc + bias) of a 256-wide accumulator -> 8 shared-memory A chunks, 16 features per half
+    auto gen_chunks = [&](uint32_t src_col, int bias_off) {
       for (int c = 0; c < 8; ++c) {
         const int b = cu & 1;
         mbar_wait(&bars[CH_EMPTY + b], ((cu >> 1) & 1) ^ 1);
         float v[16];
-        tmem_ld16(lane_t + C_SA + 32 * c + 16 * h, reinterpret_cast<uint32_t*>(v));
+        tmem_ld16(lane_t + src_col + 32 * c + 16 * h, reinterpret_cast<uint32_t*>(v));
         tmem_wait_ld();
-        bias_relu16(v, sm_small + so.b_d0 + 32 * c + 16 * h);
+        bias_relu16(v, sm_small + bias_off + 32 * c + 16 * h);
         store_chunk16(smem + SM_CHUNK + b * CHUNK_BYTES, p, 4 * h, v);
         fence_async_smem();
         warp_arrive(&bars[CH_FULL + b]);
@@ -243,12 +261,21 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
         mbar_wait(&bars[D0_FULL], ph);
         PROF_MARK(2);
         fence_after_sync();
-        gen_chunks();
+        gen_chunks(C_SA, so.b_d0);
         PROF_MARK(3);
         // ---- E2: r2 = relu(D1 + b) -> TMEM A operand [0,128) hi, [128,256) lo   (64 columns per half)
         mbar_wait(&bars[D1_FULL], ph);
         PROF_MARK(4);
         fence_after_sync();
+        float au[KIN];  // owners: (Wc r1)[j], kept in registers until the end of the step
+        if (h == 0) {
+          float yp[NY];
+          if constexpr (NY == 16) tmem_ld16(lane_t + C_Y0P, reinterpret_cast<uint32_t*>(yp));
+          else tmem_ld32(lane_t + C_Y0P, reinterpret_cast<uint32_t*>(yp));
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < KIN; ++j) au[j] = yp[j];
+        }
 #pragma unroll 1
         for (int cb = 2 * h; cb < 2 * h + 2; ++cb) {
           float v[32];
@@ -314,64 +341,30 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
         for (int j = 0; j < KIN; ++j) eps[j] = 0.f;
         if (h == 1 && live) draw_noise_reg<KIN>(a, m, k, eps);
         PROF_MARK(1);
-        // ---- E6: y1 = relu(D4 + b_u1) in place   (128 columns per half)
+        // ---- E6: y1 = relu(D4 + b_u1) -> 8 shared-memory A chunks for the folded up_0 (N = NY)
         mbar_wait(&bars[D4A_FULL], ph);
         PROF_MARK(8);
         fence_after_sync();
-#pragma unroll 1
-        for (int cb = 4 * h; cb < 4 * h + 4; ++cb) {
-          float v[32];
-          tmem_ld32(lane_t + C_D4 + 32 * cb, reinterpret_cast<uint32_t*>(v));
-          tmem_wait_ld();
-          bias_relu32(v, sm_small + so.b_u1 + 32 * cb);
-          tmem_st32(lane_t + C_D4 + 32 * cb, reinterpret_cast<const uint32_t*>(v));
-        }
-        tmem_wait_st();
-        fence_before_sync();
-        warp_arrive(&bars[Y1_FULL]);
-        PROF_MARK(9);
-        // ---- E7: r1 chunks again for res_1
-        mbar_wait(&bars[D0B_FULL], ph);
-        PROF_MARK(10);
-        fence_after_sync();
-        gen_chunks();
+        gen_chunks(C_D4, so.b_u1);
         PROF_MARK(11);
-        // ---- E8: o1 = D4 + b_r1; partial up_0 over this half's 128 columns
-        mbar_wait(&bars[D4B_FULL], ph);
+        // ---- E8: y0 = W_u0 y1 (TMEM [0,NY)) + Wc r1 (registers) + bc
+        mbar_wait(&bars[Y0_FULL], ph);
         PROF_MARK(12);
         fence_after_sync();
-        float au[KIN];
-#pragma unroll
-        for (int j = 0; j < KIN; ++j) au[j] = 0.f;
-#pragma unroll 1
-        for (int cb = 8 * h; cb < 8 * h + 8; ++cb) {  // 16 columns at a time
-          float v[16];
-          tmem_ld16(lane_t + C_D4 + 16 * cb, reinterpret_cast<uint32_t*>(v));
+        if (h == 0) {
+          float yp[NY];
+          if constexpr (NY == 16) tmem_ld16(lane_t + C_Y0, reinterpret_cast<uint32_t*>(yp));
+          else tmem_ld32(lane_t + C_Y0, reinterpret_cast<uint32_t*>(yp));
           tmem_wait_ld();
-          const float* br = sm_small + so.b_r1 + 16 * cb;
-          const float* wu = sm_small + so.u0t + (16 * cb) * KIN;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float o = v[j] + br[j];
-#pragma unroll
-            for (int q = 0; q < KIN / 4; ++q) {
-              const float4 w = *reinterpret_cast<const float4*>(wu + j * KIN + 4 * q);
-              au[4 * q] = fmaf(w.x, o, au[4 * q]);
-              au[4 * q + 1] = fmaf(w.y, o, au[4 * q + 1]);
-              au[4 * q + 2] = fmaf(w.z, o, au[4 * q + 2]);
-              au[4 * q + 3] = fmaf(w.w, o, au[4 * q + 3]);
-            }
-          }
+          for (int j = 0; j < KIN; ++j) au[j] += yp[j];
         }
         fence_before_sync();  // orders the TMEM reads before the next step's MMAs (via XIN_FULL)
         PROF_MARK(13);
-        // helpers hand their partial sums and the noise to the owners through the idle chunk buffer
+        // helpers hand the noise to the owners through the idle chunk buffer
         if (h == 1) {
 #pragma unroll
-          for (int j = 0; j < KIN; ++j) {
-            stage_f[j * TP + p] = au[j];
-            stage_f[(KIN + j) * TP + p] = eps[j];
-          }
+          for (int j = 0; j < KIN; ++j) stage_f[j * TP + p] = eps[j];
         }
         e_sync();
         PROF_MARK(15);
@@ -384,8 +377,8 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
             float ar = fmaf(wr[0], tk, sm_small[so.b_r0 + j]);
 #pragma unroll
             for (int c = 1; c < KIN; ++c) ar = fmaf(wr[c], x[c - 1], ar);
-            gv[j] = fmaxf(au[j] + stage_f[j * TP + p] + sm_small[so.b_u0 + j], 0.f) + ar;
-            eps[j] = stage_f[(KIN + j) * TP + p];
+            gv[j] = fmaxf(au[j] + sm_small[so.bc + j], 0.f) + ar;
+            eps[j] = stage_f[j * TP + p];
           }
           const float dt = __ldg(a.step_tab + k), sq_ldt = __ldg(a.step_tab + K + k);
           const float dt_l = __ldg(a.step_tab + 2 * K + k), sq_dtl = __ldg(a.step_tab + 3 * K + k);
@@ -496,6 +489,7 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
         const uint32_t wb = wait_w();
         if (elect_one()) {
           issue_block_ss<H1, 32>(tm + C_D1, chunk_s + b * CHUNK_BYTES, CHUNK_HALF, wb, c == 0);
+          issue_block_ss<NY, 32>(tm + C_Y0P, chunk_s + b * CHUNK_BYTES, CHUNK_HALF, wb + MAIN_BYTES, c == 0);
           commit(&bars[CH_EMPTY + b]);
         }
         __syncwarp();
@@ -557,34 +551,24 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
       if (elect_one()) commit(&bars[D4A_FULL]);
       __syncwarp();
       PROF_MARK(7);
-      // down_0 again into [0,256) once up_1 has finished reading o2 from there
-      mbar_wait(&bars[D4A_FULL], ph);
-      PROF_MARK(8);
-      fence_after_sync();
-      down0();
-      if (elect_one()) commit(&bars[D0B_FULL]);
-      __syncwarp();
-      PROF_MARK(9);
-      // ---- M6: res_1 on top of relu(y1), A = r1 chunks, 16 blocks of K = 16
-      mbar_wait(&bars[Y1_FULL], ph);
-      PROF_MARK(10);
-      fence_after_sync();
-      for (int c = 0; c < 8; ++c) {
-        const uint32_t b = cm & 1;
-        mbar_wait(&bars[CH_FULL + b], (cm >> 1) & 1);
-        fence_after_sync();
-        for (int j = 0; j < 2; ++j) {
-          const uint32_t wb = wait_w();
+      // ---- M6: folded up_0 = W_u0 y1 into [0,NY), A = y1 chunks (E produces them only after D4A_FULL,
+      //      i.e. once up_1 has finished reading o2 from there), 8 blocks of K = 32
+      for (int u = 0; u < NU0; ++u) {
+        const uint32_t wb = wait_w();
+        for (int cc = 0; cc < BPS; ++cc) {
+          const uint32_t b = cm & 1;
+          mbar_wait(&bars[CH_FULL + b], (cm >> 1) & 1);
+          fence_after_sync();
           if (elect_one()) {
-            issue_block_ss<H0, 16>(tm + C_D4, chunk_s + b * CHUNK_BYTES + j * 2 * ACT_KSTEP, CHUNK_HALF, wb, false);
-            if (j == 1) commit(&bars[CH_EMPTY + b]);
+            issue_block_ss<NY, 32>(tm + C_Y0, chunk_s + b * CHUNK_BYTES, CHUNK_HALF, wb + cc * (NY * 256), u == 0 && cc == 0);
+            commit(&bars[CH_EMPTY + b]);
           }
           __syncwarp();
-          release_w();
+          ++cm;
         }
-        ++cm;
+        release_w();
       }
-      if (elect_one()) commit(&bars[D4B_FULL]);
+      if (elect_one()) commit(&bars[Y0_FULL]);
       __syncwarp();
       PROF_MARK(11);
     }
@@ -597,8 +581,8 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
       for (uint32_t i = 0; i < total; ++i) {
         const uint32_t s = i % NSTAGE;
         mbar_wait(&bars[W_EMPTY + s], ((i / NSTAGE) & 1) ^ 1);
-        const int slot = fwd_stage_slot(d, (int)in_step);
-        const uint32_t bytes = slot < S0 ? (uint32_t)(2 * (H0 / S0) * KIN * 4) : (uint32_t)SLOT_BYTES;
+        const int slot = (int)in_step;
+        const uint32_t bytes = fwd_slot_bytes(d, slot);
         mbar_expect_tx(&bars[W_FULL + s], bytes);
         bulk_g2s(smem + SM_RING + s * SLOT_BYTES, tape + (size_t)slot * SLOT_BYTES, bytes, &bars[W_FULL + s]);
         if (++in_step == NS) in_step = 0;
@@ -607,7 +591,7 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
     __syncwarp();
   }
 
-  // ---- teardown: every MMA has completed (E waited for the last D4B_FULL)
+  // ---- teardown: every MMA has completed (E waited for the last Y0_FULL)
   fence_before_sync();
   __syncthreads();
   if (warp == 8) tmem_dealloc(tm, 512);
@@ -619,8 +603,12 @@ extern "C" int socm_debug_tc_prof(unsigned long long* out32) {
 }
 #endif
 
-int pack_tc(const socm_unet* net, unsigned char* tape, float* small, bool with_bwd, cudaStream_t stream) {
-  pack_tc_kernel<<<96, 256, 0, stream>>>(*net, tape, small, with_bwd ? 1 : 0);
+int pack_tc(const socm_unet* net, unsigned char* tape, bool with_bwd, cudaStream_t stream) {
+  float* small = tc_small_ptr(tape, net->d, with_bwd);
+  float* wc = tc_wc_ptr(tape, net->d, with_bwd);
+  fold_tc_kernel<<<32, H0, 0, stream>>>(*net, wc, small);
+  SOCM_LAUNCH_CHECK();
+  pack_tc_kernel<<<96, 256, 0, stream>>>(*net, wc, tape, small, with_bwd ? 1 : 0);
   SOCM_LAUNCH_CHECK();
   return SOCM_OK;
 }
@@ -631,8 +619,8 @@ bool rollout_tc_supported(const socm_unet* net) { return is_default_arch(net) &&
 int launch_rollout_tc(const RolloutArgs& a, const socm_unet* net, void* workspace, cudaStream_t stream) {
   const int d = a.st.d;
   unsigned char* tape = static_cast<unsigned char*>(workspace);
-  float* small = reinterpret_cast<float*>(tape + (size_t)fwd_slots(d) * SLOT_BYTES);
-  if (int rc = pack_tc(net, tape, small, false, stream)) return rc;
+  float* small = tc_small_ptr(tape, d, false);
+  if (int rc = pack_tc(net, tape, false, stream)) return rc;
   const int smem = rollout_tc_smem_bytes(d);
   const int n_tiles = (a.B + TP - 1) / TP;
   const int grid = n_tiles < sm_count() ? n_tiles : sm_count();

@@ -56,7 +56,7 @@ __global__ void pack_target_tape_kernel(const float* __restrict__ L, int nrows, 
     int nt = 0;
     while (s >= plan.slot_begin[nt + 1]) ++nt;
     const int k0 = 16 * (2 * plan.chunk_begin[nt] + (s - plan.slot_begin[nt]));
-    unsigned char* base = tape + (size_t)s * SLOT_BYTES;
+    unsigned char* base = tape + (size_t)s * MAIN_BYTES;
     for (int i = threadIdx.x; i < K2_NB * 16; i += blockDim.x) {
       const int n = i >> 4, k = i & 15;
       const int row = nt * K2_NB + n, col = k0 + k;
@@ -71,7 +71,7 @@ __global__ void pack_target_tape_kernel(const float* __restrict__ L, int nrows, 
 
 namespace k2 {
 constexpr int SM_RING = 0;
-constexpr int SM_CHUNK = SM_RING + NSTAGE * SLOT_BYTES;
+constexpr int SM_CHUNK = SM_RING + NSTAGE * MAIN_BYTES;
 constexpr int SM_BARS = SM_CHUNK + 2 * CHUNK_BYTES;
 enum Bar { W_FULL = 0, W_EMPTY = W_FULL + NSTAGE, CH_FULL = W_EMPTY + NSTAGE, CH_EMPTY = CH_FULL + 2,
            ACC_FULL = CH_EMPTY + 2, ACC_EMPTY = ACC_FULL + 2, N_BARS = ACC_EMPTY + 2 };
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(K2_NT, 1)
               fence_after_sync();
               if (elect_one()) {
                 issue_block_ss<K2_NB, 16>(tm + a * 256, chunk_s + b * CHUNK_BYTES + j * 2 * ACT_KSTEP, CHUNK_HALF,
-                                          ring_s + s * SLOT_BYTES, c == c0 && j == 0);
+                                          ring_s + s * MAIN_BYTES, c == c0 && j == 0);
                 if (j == 1) commit(&bars[CH_EMPTY + b]);
                 commit(&bars[W_EMPTY + s]);
               }
@@ -219,8 +219,8 @@ __global__ void __launch_bounds__(K2_NT, 1)
       for (uint64_t i = 0; i < total; ++i) {
         const uint32_t s = (uint32_t)(i % NSTAGE);
         mbar_wait(&bars[W_EMPTY + s], (uint32_t)((i / NSTAGE) & 1) ^ 1);
-        mbar_expect_tx(&bars[W_FULL + s], SLOT_BYTES);
-        bulk_g2s(smem + SM_RING + s * SLOT_BYTES, tape + (size_t)slot * SLOT_BYTES, SLOT_BYTES, &bars[W_FULL + s]);
+        mbar_expect_tx(&bars[W_FULL + s], MAIN_BYTES);
+        bulk_g2s(smem + SM_RING + s * MAIN_BYTES, tape + (size_t)slot * MAIN_BYTES, MAIN_BYTES, &bars[W_FULL + s]);
         if (++slot == per_tile) slot = 0;
       }
     }
@@ -239,7 +239,7 @@ using namespace socm;
 extern "C" int64_t socm_target_gemm_tc_workspace_bytes(int32_t K, int32_t d) {
   if (K < 1 || d < 1) return -1;
   const tc::K2Plan p = tc::make_plan((K + 1) * d, (2 * K + 1) * d, d);
-  return (int64_t)p.slot_begin[p.n_blocks] * tc::SLOT_BYTES + 1024;
+  return (int64_t)p.slot_begin[p.n_blocks] * tc::MAIN_BYTES + 1024;
 }
 
 extern "C" int socm_target_gemm_tc_f32(const float* L, const float* R, int32_t B, int32_t K, int32_t d, int32_t ldr,

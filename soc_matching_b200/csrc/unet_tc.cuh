@@ -34,78 +34,104 @@ namespace tc {
 
 constexpr int TP = 128;  // points per tile
 constexpr int H0 = 256, H1 = 128, H2 = 64;
-constexpr int SLOT_BYTES = 32768;  // one tape slot / ring stage: hi slab + lo slab of a weight block
+constexpr int MAIN_BYTES = 32768;  // main weight block of a tape slot: hi slab + lo slab
+constexpr int SLOT_BYTES = 40960;  // tape slot stride / ring stage: main block + (down_1 slots) the folded Wc block
 constexpr int NSTAGE = 3;
 constexpr int CHUNK_F = 32;                   // features per shared-memory activation chunk
 constexpr int CHUNK_HALF = TP * CHUNK_F * 4;  // bytes of the hi (or lo) part of a chunk
 constexpr int CHUNK_BYTES = 2 * CHUNK_HALF;
 constexpr int MAX_KIN = 24;                   // d + 1 rounded up to 8; the engine covers d <= 23
+constexpr int WC_LAYER = 9;                   // pseudo layer index of the folded matrix Wc = W_up0 W_res1  [d][256]
 
 __host__ __device__ inline int kin_of(int d) { return ((d + 1 + 7) / 8) * 8; }
 __host__ __device__ inline int w0_slots(int d) { return kin_of(d) > 16 ? 2 : 1; }
+// N of the folded last-layer MMAs (output features of up_0, padded to a legal N for M = 128)
+__host__ __device__ inline int ny_of(int d) { return kin_of(d) <= 16 ? 16 : 32; }
+__host__ __device__ inline int u0_slots(int d) { return ny_of(d) == 16 ? 1 : 2; }
 
-// ---------------------------------------------------------------- forward weight tape
-// slot order: [down_0 x S] [down_1 x 8] [down_2 x 2] [up_2 x 2] [res_2 x 4] [up_1 x 8] [res_1 x 16]
+// ---------------------------------------------------------------- folding res_1 into up_0
+// models.py:239-241:  o1 = relu(up_1 o2) + res_1 r1,  out0 = relu(up_0 o1) + res_0 x.  There is no
+// non-linearity between res_1 and up_0, so
+//     up_0 o1 = W_u0 y1 + Wc r1 + bc,     Wc = W_u0 W_r1  [d x 256],  bc = W_u0 b_r1 + b_u0,  y1 = relu(up_1 o2)
+// and the K = N = 256 res_1 GEMM (39 % of the network's FLOPs) is never evaluated per point: Wc r1
+// rides on the r1 chunks that feed down_1 (an extra N = 16 MMA per chunk), and in the backward pass
+//     d_r1 += Wc^T d_y0 (K = d),   dW_r1 = W_u0^T S,   dW_u0 = d_y0^T y1 + S W_r1^T + (sum d_y0) b_r1^T,   S = d_y0^T r1.
+//
+// ---------------------------------------------------------------- weight tapes
+// forward slots: [down_0 x S] [down_1 x 8, each followed by its Wc block] [down_2 x 2] [up_2 x 2] [res_2 x 4]
+//                [up_1 x 8] [up_0 x U: 8 K-chunks of 32, several per slot]
+// backward slots (W^T blocks): [up_0^T x S] [up_1^T x 8] [res_2^T x 4] [up_2^T x 2] [down_2^T x 2] [down_1^T x 8] [Wc^T x S]
 struct SlotDesc {
-  int layer;  // index into socm_unet::w
+  int layer;  // index into socm_unet::w, or WC_LAYER
   int n0, N;  // rows of the block (N side of the MMA)
   int k0, Kc; // contraction range of the block (Kc multiple of 8)
-  int ktot;   // row length of the nn.Linear weight W[out][ktot]
+  int ktot;   // row length of the weight matrix W[out][ktot]
   int transposed;  // 0: B[n][k] = W[n0+n][k0+k] (forward);  1: B[n][k] = W[k0+k][n0+n] (dgrad: W^T)
   int klim;   // contraction indices >= klim are zero padding
+  int nlim;   // rows >= nlim are zero padding
 };
-__host__ __device__ inline int fwd_slots(int d) { return 40 + w0_slots(d); }
-__host__ __device__ inline SlotDesc fwd_slot(int d, int s) {
-  const int S = w0_slots(d), kin = kin_of(d);
-  if (s < S) return SlotDesc{0, s * (H0 / S), H0 / S, 0, kin, d + 1, 0, d + 1};
-  s -= S;
-  if (s < 8) return SlotDesc{1, 0, H1, 32 * s, 32, H0, 0, H0};
-  s -= 8;
-  if (s < 2) return SlotDesc{2, 0, H2, 64 * s, 64, H1, 0, H1};
-  s -= 2;
-  if (s < 2) return SlotDesc{6, 0, H1, 32 * s, 32, H2, 0, H2};
-  s -= 2;
-  if (s < 4) return SlotDesc{5, 0, H1, 32 * s, 32, H1, 0, H1};
-  s -= 4;
-  if (s < 8) return SlotDesc{7, 0, H0, 16 * s, 16, H1, 0, H1};
-  s -= 8;
-  return SlotDesc{4, 0, H0, 16 * s, 16, H0, 0, H0};
+struct PackItem {
+  int slot, byte_off;
+  SlotDesc sd;
+};
+constexpr int NOLIM = 1 << 30;
+__host__ __device__ inline int fwd_slots(int d) { return w0_slots(d) + 24 + u0_slots(d); }
+__host__ __device__ inline int bwd_slots(int d) { return 2 * w0_slots(d) + 24; }
+__host__ __device__ inline int fwd_items(int d) { return w0_slots(d) + 40; }
+__host__ __device__ inline int bwd_items(int d) { return bwd_slots(d); }
+__host__ __device__ inline PackItem fwd_item(int d, int i) {
+  const int S = w0_slots(d), kin = kin_of(d), NY = ny_of(d);
+  if (i < S) return PackItem{i, 0, SlotDesc{0, i * (H0 / S), H0 / S, 0, kin, d + 1, 0, d + 1, NOLIM}};
+  i -= S;
+  if (i < 8) return PackItem{S + i, 0, SlotDesc{1, 0, H1, 32 * i, 32, H0, 0, H0, NOLIM}};
+  i -= 8;
+  if (i < 8) return PackItem{S + i, MAIN_BYTES, SlotDesc{WC_LAYER, 0, NY, 32 * i, 32, H0, 0, H0, d}};
+  i -= 8;
+  if (i < 2) return PackItem{S + 8 + i, 0, SlotDesc{2, 0, H2, 64 * i, 64, H1, 0, H1, NOLIM}};
+  i -= 2;
+  if (i < 2) return PackItem{S + 10 + i, 0, SlotDesc{6, 0, H1, 32 * i, 32, H2, 0, H2, NOLIM}};
+  i -= 2;
+  if (i < 4) return PackItem{S + 12 + i, 0, SlotDesc{5, 0, H1, 32 * i, 32, H1, 0, H1, NOLIM}};
+  i -= 4;
+  if (i < 8) return PackItem{S + 16 + i, 0, SlotDesc{7, 0, H0, 16 * i, 16, H1, 0, H1, NOLIM}};
+  i -= 8;
+  const int bps = MAIN_BYTES / (NY * 256);  // up_0 K-chunks per slot (8 or 4)
+  return PackItem{S + 24 + i / bps, (i % bps) * (NY * 256), SlotDesc{8, 0, NY, 32 * i, 32, H0, 0, H0, d}};
 }
-// ---- backward (dgrad) tape: W^T blocks in the order the backward pass consumes them
-// [up_0^T x S] [up_1^T x 8] [res_2^T x 4] [up_2^T x 2] [down_2^T x 2] [down_1^T x 8] [res_1^T x 16]
-// (same block shapes as the forward tape, so the same issue code serves both)
-__host__ __device__ inline SlotDesc bwd_slot(int d, int s) {
+__host__ __device__ inline PackItem bwd_item(int d, int s) {
   const int S = w0_slots(d), kin = kin_of(d);
-  if (s < S) return SlotDesc{8, s * (H0 / S), H0 / S, 0, kin, H0, 1, d};  // d_o1[f] = sum_j d_y0[j] W_u0[j][f]
+  const int slot = s;
+  if (s < S) return PackItem{slot, 0, SlotDesc{8, s * (H0 / S), H0 / S, 0, kin, H0, 1, d, NOLIM}};  // d_o1[f] = sum_j d_y0[j] W_u0[j][f]
   s -= S;
-  if (s < 8) return SlotDesc{7, 0, H1, 32 * s, 32, H1, 1, H0};   // d_o2[c] = sum_n d_y1[n] W_u1[n][c]
+  if (s < 8) return PackItem{slot, 0, SlotDesc{7, 0, H1, 32 * s, 32, H1, 1, H0, NOLIM}};   // d_o2[c] = sum_n d_y1[n] W_u1[n][c]
   s -= 8;
-  if (s < 4) return SlotDesc{5, 0, H1, 32 * s, 32, H1, 1, H1};   // d_r2[c] = sum_n d_o2[n] W_r2[n][c]
+  if (s < 4) return PackItem{slot, 0, SlotDesc{5, 0, H1, 32 * s, 32, H1, 1, H1, NOLIM}};   // d_r2[c] = sum_n d_o2[n] W_r2[n][c]
   s -= 4;
-  if (s < 2) return SlotDesc{6, 0, H2, 64 * s, 64, H2, 1, H1};   // d_r3[c] = sum_n d_y2[n] W_u2[n][c]
+  if (s < 2) return PackItem{slot, 0, SlotDesc{6, 0, H2, 64 * s, 64, H2, 1, H1, NOLIM}};   // d_r3[c] = sum_n d_y2[n] W_u2[n][c]
   s -= 2;
-  if (s < 2) return SlotDesc{2, 0, H1, 32 * s, 32, H1, 1, H2};   // d_r2[c] += sum_n d_z3[n] W_d2[n][c]
+  if (s < 2) return PackItem{slot, 0, SlotDesc{2, 0, H1, 32 * s, 32, H1, 1, H2, NOLIM}};   // d_r2[c] += sum_n d_z3[n] W_d2[n][c]
   s -= 2;
-  if (s < 8) return SlotDesc{1, 0, H0, 16 * s, 16, H0, 1, H1};   // d_r1[c] = sum_n d_z2[n] W_d1[n][c]
+  if (s < 8) return PackItem{slot, 0, SlotDesc{1, 0, H0, 16 * s, 16, H0, 1, H1, NOLIM}};   // d_r1[c] = sum_n d_z2[n] W_d1[n][c]
   s -= 8;
-  return SlotDesc{4, 0, H0, 16 * s, 16, H0, 1, H0};              // d_r1[c] += sum_n d_o1[n] W_r1[n][c]
+  return PackItem{slot, 0, SlotDesc{WC_LAYER, s * (H0 / S), H0 / S, 0, kin, H0, 1, d, NOLIM}};  // d_r1[g] += sum_j d_y0[j] Wc[j][g]
 }
-__host__ __device__ inline int slot_bytes(const SlotDesc& sd) { return 2 * sd.N * sd.Kc * 4; }
-
-// stage i of a forward pass (the consumption order repeats down_0 before res_1) -> tape slot
-__host__ __device__ inline int fwd_stages(int d) { return 40 + 2 * w0_slots(d); }
-__host__ __device__ inline int fwd_stage_slot(int d, int i) {
+// bytes the producer copies for a slot
+__host__ __device__ inline uint32_t fwd_slot_bytes(int d, int s) {
   const int S = w0_slots(d);
-  if (i < S + 24) return i;
-  if (i < 2 * S + 24) return i - (S + 24);
-  return i - S;
+  if (s < S) return (uint32_t)(2 * (H0 / S) * kin_of(d) * 4);
+  if (s < S + 8) return (uint32_t)(MAIN_BYTES + 2 * ny_of(d) * 32 * 4);
+  return (uint32_t)MAIN_BYTES;
+}
+__host__ __device__ inline uint32_t bwd_slot_bytes(int d, int s) {
+  const int S = w0_slots(d);
+  if (s < S || s >= S + 24) return (uint32_t)(2 * (H0 / S) * kin_of(d) * 4);
+  return (uint32_t)MAIN_BYTES;
 }
 
 // ---------------------------------------------------------------- small block (floats, fp32, read from shared memory)
 struct SmallTc {
-  int b_d0, b_d1, b_d2, b_u2, b_r2, b_u1, b_r1;
-  int u0t;   // up_0^T [256][kin]  (zero padded: the per-point loops run over kin lanes without predicates)
-  int b_u0;  // [kin]
+  int b_d0, b_d1, b_d2, b_u2, b_r2, b_u1;
+  int bc;    // [kin]  folded bias W_u0 b_r1 + b_u0
   int r0;    // res_0 [kin][kin]   (zero padded rows and columns; column 0 multiplies t)
   int b_r0;  // [kin]
   int total;
@@ -120,17 +146,26 @@ __host__ __device__ inline SmallTc small_tc(int d) {
   o.b_u2 = p; p += H1;
   o.b_r2 = p; p += H1;
   o.b_u1 = p; p += H0;
-  o.b_r1 = p; p += H0;
-  o.u0t = p; p += H0 * kin;
-  o.b_u0 = p; p += kin;
+  o.bc = p; p += kin;
   o.r0 = p; p += kin * kin;
   o.b_r0 = p; p += kin;
   o.total = ((p + 3) / 4) * 4;
   return o;
 }
-// workspace: [tape: fwd_slots (+ fwd_slots backward slots) x SLOT_BYTES][small block]
+// workspace: [tape: (fwd_slots (+ bwd_slots)) x SLOT_BYTES][small block][Wc: 32 x 256 floats]
+constexpr int WC_FLOATS = 32 * H0;
+__host__ __device__ inline int64_t tc_tape_bytes(int d, bool with_bwd) {
+  return (int64_t)(fwd_slots(d) + (with_bwd ? bwd_slots(d) : 0)) * SLOT_BYTES;
+}
 __host__ __device__ inline int64_t tc_workspace_bytes(int d, bool with_bwd = false) {
-  return (int64_t)fwd_slots(d) * (with_bwd ? 2 : 1) * SLOT_BYTES + (int64_t)small_tc(d).total * 4;
+  return tc_tape_bytes(d, with_bwd) + (int64_t)small_tc(d).total * 4 + (int64_t)WC_FLOATS * 4;
+}
+
+__host__ __device__ inline float* tc_small_ptr(unsigned char* tape, int d, bool with_bwd) {
+  return reinterpret_cast<float*>(tape + tc_tape_bytes(d, with_bwd));
+}
+__host__ __device__ inline float* tc_wc_ptr(unsigned char* tape, int d, bool with_bwd) {
+  return tc_small_ptr(tape, d, with_bwd) + small_tc(d).total;
 }
 
 // canonical no-swizzle K-major offsets (bytes)

@@ -32,12 +32,10 @@ struct LayerBlock {
   int kind;          // output mapping, see flush()
   int layer, row0;   // socm_unet layer index of the weights, first output row
 };
-enum { OUT_DIRECT = 0, OUT_TRANSPOSED = 1, OUT_XIN = 2, OUT_SMALL = 3, OUT_BIAS_ONLY = 4 };
+enum { OUT_DIRECT = 0, OUT_TRANSPOSED = 1, OUT_XIN = 2, OUT_SMALL = 3, OUT_BIAS_ONLY = 4, OUT_AUX_S = 5 };
 constexpr int N_LB = 14;
 __constant__ LayerBlock c_lb[N_LB] = {
     {FB_DZ2, 128, FB_R1, 256, 1, OUT_DIRECT, 1, 0},        // down_1  (+ bias from d_z2)
-    {FB_DO1, 128, FB_R1, 256, 1, OUT_DIRECT, 4, 0},        // res_1 rows 0..127
-    {FB_DO1 + 4, 128, FB_R1, 256, 1, OUT_DIRECT, 4, 128},  // res_1 rows 128..255
     {FB_DY1, 128, FB_O2, 128, 1, OUT_DIRECT, 7, 0},        // up_1
     {FB_DY1 + 4, 128, FB_O2, 128, 1, OUT_DIRECT, 7, 128},
     {FB_DO2, 128, FB_R2, 128, 1, OUT_DIRECT, 5, 0},        // res_2
@@ -45,8 +43,10 @@ __constant__ LayerBlock c_lb[N_LB] = {
     {FB_R2, 128, FB_DZ3, 64, 0, OUT_TRANSPOSED, 2, 0},     // down_2: D[in][out]
     {FB_DZ1, 128, FB_XIN, 32, 0, OUT_XIN, 0, 0},           // down_0 rows 0..127 (+ bias via the ones feature)
     {FB_DZ1 + 4, 128, FB_XIN, 32, 0, OUT_XIN, 0, 128},
-    {FB_O1, 128, FB_DY0, 32, 0, OUT_TRANSPOSED, 8, 0},     // up_0: D[in][out]
-    {FB_O1 + 4, 128, FB_DY0, 32, 0, OUT_TRANSPOSED, 8, 128},
+    {FB_Y1, 128, FB_DY0, 32, 0, OUT_TRANSPOSED, 8, 0},     // up_0, y1 part: D[in][out] = (d_y0^T y1)^T
+    {FB_Y1 + 4, 128, FB_DY0, 32, 0, OUT_TRANSPOSED, 8, 128},
+    {FB_R1, 128, FB_DY0, 32, 0, OUT_AUX_S, 8, 0},          // S^T = (d_y0^T r1)^T -> aux (res_1 / up_0 via fold_finish_kernel)
+    {FB_R1 + 4, 128, FB_DY0, 32, 0, OUT_AUX_S, 8, 128},
     // M is always 128 (an M = 64 accumulator is spread over 16 lanes per TMEM quarter); the extra rows
     // belong to the neighbouring tensors of the scratch and are ignored by the flush
     {FB_DY0, 128, FB_XIN, 32, 0, OUT_SMALL, 3, 0},         // rows 0..31 d_y0 -> b(up_0); rows 32..63 d_o0 -> res_0, b(res_0)
@@ -71,7 +71,7 @@ __device__ __forceinline__ void red_add(float* p, float v) {
 }
 
 __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char* __restrict__ scratch, int n_tiles,
-                                                            int d, float* __restrict__ grad) {
+                                                            int d, float* __restrict__ grad, float* __restrict__ aux) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // stage bases must be 512-byte aligned in the shared window: the operand swizzle uses address bits 7-8
   unsigned char* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
@@ -259,6 +259,10 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
 #pragma unroll
             for (int j = 0; j < 16; ++j)
               if (c0 + j < n_out) red_add(grad + go.w[lb.layer] + (size_t)(c0 + j) * in_total + row, v[j]);
+          } else if (lb.kind == OUT_AUX_S) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < d) red_add(aux + AUX_S + (c0 + j) * 256 + row, v[j]);
           } else if (lb.kind == OUT_XIN) {
             // down_0: D[out = row][k]: k <= d -> weight, k = ONES_FEATURE -> bias
 #pragma unroll
@@ -273,7 +277,10 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
             for (int j = 0; j < 16; ++j) {
               const int k = c0 + j;
               if (r < 32) {
-                if (r < d && k == ONES_FEATURE) red_add(grad + go.b[8] + r, v[j]);
+                if (r < d && k == ONES_FEATURE) {
+                  red_add(grad + go.b[8] + r, v[j]);
+                  red_add(aux + AUX_SB + r, v[j]);
+                }
               } else if (r < 64 && r - 32 < d) {
                 if (k <= d) red_add(grad + go.w[3] + (size_t)(r - 32) * (d + 1) + k, v[j]);
                 if (k == ONES_FEATURE) red_add(grad + go.b[3] + (r - 32), v[j]);
@@ -302,11 +309,11 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
   if (warp == 4) tmem_dealloc(tm, 512);
 }
 
-int launch_wgrad_tc(const unsigned char* scratch, int n_tiles, int d, float* grad, cudaStream_t stream) {
+int launch_wgrad_tc(const unsigned char* scratch, int n_tiles, int d, float* grad, float* aux, cudaStream_t stream) {
   if (n_tiles <= 0) return SOCM_OK;
   SOCM_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
   const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-  wgrad_tc_kernel<<<grid, WG_NT, WG_SMEM, stream>>>(scratch, n_tiles, d, grad);
+  wgrad_tc_kernel<<<grid, WG_NT, WG_SMEM, stream>>>(scratch, n_tiles, d, grad, aux);
   SOCM_LAUNCH_CHECK();
   return SOCM_OK;
 }
@@ -315,8 +322,8 @@ int launch_wgrad_tc(const unsigned char* scratch, int n_tiles, int d, float* gra
 }  // namespace socm
 
 // debug / test entry: run K3b on a caller-built scratch (tests/test_gpu_wgrad_tc.py)
-extern "C" int socm_debug_wgrad_tc(const void* scratch, int32_t n_tiles, int32_t d, float* grad, void* stream) {
-  return socm::tc::launch_wgrad_tc(static_cast<const unsigned char*>(scratch), n_tiles, d, grad,
+extern "C" int socm_debug_wgrad_tc(const void* scratch, int32_t n_tiles, int32_t d, float* grad, float* aux, void* stream) {
+  return socm::tc::launch_wgrad_tc(static_cast<const unsigned char*>(scratch), n_tiles, d, grad, aux,
                                    static_cast<cudaStream_t>(stream));
 }
 extern "C" int64_t socm_debug_wgrad_tile_bytes(void) { return socm::tc::TILE_BYTES; }

@@ -10,11 +10,10 @@ from helpers import rel_l2
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
-FB = dict(XIN=0, R1=1, R2=9, R3=13, O2=15, O1=19, DY0=27, DO0=28, DY1=29, DO1=37, DY2=45, DO2=49, DZ3=53, DZ2=55,
-          DZ1=59)
-WIDTH = dict(XIN=32, R1=256, R2=128, R3=64, O2=128, O1=256, DY0=32, DO0=32, DY1=256, DO1=256, DY2=128, DO2=128,
+FB = dict(XIN=0, R1=1, R2=9, R3=13, O2=15, Y1=19, DY0=27, DO0=28, DY1=29, DY2=37, DO2=41, DZ3=45, DZ2=47, DZ1=51)
+WIDTH = dict(XIN=32, R1=256, R2=128, R3=64, O2=128, Y1=256, DY0=32, DO0=32, DY1=256, DY2=128, DO2=128,
              DZ3=64, DZ2=128, DZ1=256)
-NFB = 67
+NFB = 59
 
 
 def tf32(x):
@@ -54,21 +53,35 @@ def test_wgrad_tc_matches_torch(d, n_tiles):
     nin = [d + 1, 256, 128, d + 1, 256, 128, 64, 128, 256]
     total = sum(o * i + o for o, i in zip(nout, nin))
     grad = torch.zeros(total, device=DEV)
-    _lib.check(lib.socm_debug_wgrad_tc(scratch.data_ptr(), n_tiles, d, grad.data_ptr(), _lib.stream_ptr()))
+    aux = torch.zeros(32 * 256 + 32, device=DEV)
+    _lib.check(lib.socm_debug_wgrad_tc(scratch.data_ptr(), n_tiles, d, grad.data_ptr(), aux.data_ptr(),
+                                       _lib.stream_ptr()))
     torch.cuda.synchronize()
     grad = grad.cpu()
+    aux = aux.cpu()
     dd = {k: v.double() for k, v in t.items()}
     x = dd["XIN"][:, :d + 1]
-    pairs = [("DZ1", x), ("DZ2", dd["R1"]), ("DZ3", dd["R2"]), ("DO0", x), ("DO1", dd["R1"]), ("DO2", dd["R2"]),
-             ("DY2", dd["R3"]), ("DY1", dd["O2"]), ("DY0", dd["O1"])]
+    # res_1 (layer 4) is folded into up_0 (unet_tc.cuh): K3b leaves its gradient at zero and instead
+    # accumulates S = d_y0^T r1 and sb = sum d_y0 in `aux`; up_0 (layer 8) receives d_y0^T y1 only.
+    pairs = [("DZ1", x), ("DZ2", dd["R1"]), ("DZ3", dd["R2"]), ("DO0", x), None, ("DO2", dd["R2"]),
+             ("DY2", dd["R3"]), ("DY1", dd["O2"]), ("DY0", dd["Y1"])]
     off = 0
-    for l, (dy, act) in enumerate(pairs):
-        dyv = dd[dy][:, :nout[l]]
-        want_w = dyv.t() @ act
-        want_b = dyv.sum(0)
+    for l, pr in enumerate(pairs):
         got_w = grad[off:off + nout[l] * nin[l]].reshape(nout[l], nin[l])
         off += nout[l] * nin[l]
         got_b = grad[off:off + nout[l]]
         off += nout[l]
+        if pr is None:
+            assert float(got_w.abs().max()) == 0.0 and float(got_b.abs().max()) == 0.0
+            continue
+        dy, act = pr
+        dyv = dd[dy][:, :nout[l]]
+        want_w = dyv.t() @ act
+        want_b = dyv.sum(0)
         assert rel_l2(got_w, want_w) < 1e-5, (l, dy, rel_l2(got_w, want_w))
         assert rel_l2(got_b, want_b) < 1e-5, (l, dy, "bias", rel_l2(got_b, want_b))
+    S = aux[:32 * 256].reshape(32, 256)
+    want_S = dd["DY0"][:, :d].t() @ dd["R1"]
+    assert rel_l2(S[:d], want_S) < 1e-5, rel_l2(S[:d], want_S)
+    assert float(S[d:].abs().max()) == 0.0
+    assert rel_l2(aux[32 * 256:32 * 256 + d], dd["DY0"][:, :d].sum(0)) < 1e-5
