@@ -1,0 +1,60 @@
+"""Kernel timing for A/B runs of development builds (SOCM_B200_LIB=<path> selects the library):
+K1 (rollout) and K3 (loss + backward) through the C ABI on the bench workload's shape."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+from helpers import seeded_unet
+from soc_matching_b200 import _lib, networks, simulate, sde as sde_mod
+DEV = "cuda"
+d, K = 10, 200
+B = int(os.environ.get("AB_B", 8140 * 128 // 201 // 128 * 128 * 2))
+lib = _lib.load()
+p = {k: v.to(DEV) for k, v in seeded_unet(d, [256, 128, 64], 31).items()}
+unet = networks.FullyConnectedUNet(d, (256, 128, 64), 1.0).to(DEV); unet.load_state_dict(p)
+udesc, keep = networks.unet_desc(unet)
+g = torch.Generator(DEV).manual_seed(1)
+states = torch.randn(K + 1, B, d, device=DEV, generator=g)
+ts = torch.linspace(0, 1, K + 1, device=DEV)
+ldt = ((K + 1) * d + 3) // 4 * 4
+target = torch.randn(B, ldt, device=DEV, generator=g)
+w = torch.ones(B, device=DEV)
+G = torch.zeros(B, ldt, device=DEV)
+grad = torch.zeros(int(lib.socm_unet_param_count(udesc)), device=DEV)
+loss = torch.zeros(1, device=DEV, dtype=torch.float64)
+ws = torch.zeros(int(lib.socm_loss_workspace_bytes(udesc, B, K)) // 4 + 1024, device=DEV)
+st = _lib.Setting()
+eye, kap = torch.eye(d, device=DEV), torch.ones(d, device=DEV)
+st.kind, st.d, st.sigma_is_identity, st.lmbd = 2, d, 1, 1.0
+st.sigma, st.sigma_inv, st.kappa, st.nu = eye.data_ptr(), eye.data_ptr(), kap.data_ptr(), kap.data_ptr()
+def k3():
+    _lib.check(lib.socm_unet_loss_fwdbwd_f32(st, udesc, None, ts.data_ptr(), states.data_ptr(), target.data_ptr(), ldt,
+                                             w.data_ptr(), None, 1.0, B, K, G.data_ptr(), grad.data_ptr(), loss.data_ptr(),
+                                             ws.data_ptr(), _lib.LOSS_FORCE_TC, _lib.stream_ptr()))
+def timeit(fn, n=4):
+    fn(); torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+t3 = timeit(k3)
+n_tiles = (K + 1) * (B // 128)
+print(f"{os.environ.get('SOCM_B200_LIB', 'default')}: B={B} K3 {t3:.2f} ms ({n_tiles} tiles, {t3 * 1e3 / (n_tiles / 148):.1f} us/tile/SM)", end="")
+if os.environ.get("AB_K1", "1") == "1":
+    from helpers import make_product_sde
+    try:
+        s = sde_mod.DoubleWell(d=d, device=DEV) if hasattr(sde_mod, "DoubleWell") else None
+    except Exception as e:
+        s = None
+    if s is not None:
+        try:
+            s.nabla_V = unet
+            x0 = torch.zeros(65536, d, device=DEV)
+            fn = lambda: simulate.stochastic_trajectories(s, x0, ts, 1.0)
+            t1 = timeit(fn, 3)
+            print(f"  K1 {t1:.2f} ms for 65536 paths", end="")
+        except Exception as e:
+            print("  K1 skipped:", repr(e)[:100], end="")
+print()

@@ -12,7 +12,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsocm_b200.so")
+LIB_PATH = os.environ.get("SOCM_B200_LIB") or os.path.join(_HERE, "libsocm_b200.so")  # override: A/B runs of dev builds
 
 c_float_p = C.POINTER(C.c_float)
 

@@ -24,44 +24,82 @@ namespace tc {
 
 using namespace umma;
 
-// one unit of work: D[M x N] (+ D2[M x 32] against the XIN block when with_x) over all points
-struct LayerBlock {
-  int a_fb, M;       // A operand: first feature block, rows (64 or 128)
-  int b_fb, N;       // B operand: first feature block, columns (multiple of 32)
-  int with_x;        // also multiply A with the FB_XIN block (N = 32): column ONES_FEATURE = bias gradient
-  int kind;          // output mapping, see flush()
-  int layer, row0;   // socm_unet layer index of the weights, first output row
+// ---------------------------------------------------------------- work description
+// A stage = the operands of one (tile, quarter) that a group of products shares, copied once into shared
+// memory: up to four regions  A (16 KB = 128 feature rows) | B (32 KB = 256 rows) | X (4 KB) | X2 (4 KB).
+// Every region can serve as the M = 128 operand or as the N operand of a product (the K-major swizzled
+// layout is the same for both), so e.g. r1 is at once the N operand of down_1 and, in two halves, the M
+// operand of S^T = r1^T d_y0.  Small products ride on the stages of the big ones instead of paying a
+// pipeline stage of their own (the kernel is bound by the per-stage latency, not by bytes or MMAs).
+struct Load {
+  int dst, fb, bytes;  // offset inside the raw stage, first feature block of the scratch quarter, bytes
 };
-enum { OUT_DIRECT = 0, OUT_TRANSPOSED = 1, OUT_XIN = 2, OUT_SMALL = 3, OUT_BIAS_ONLY = 4, OUT_AUX_S = 5 };
-constexpr int N_LB = 14;
-__constant__ LayerBlock c_lb[N_LB] = {
-    {FB_DZ2, 128, FB_R1, 256, 1, OUT_DIRECT, 1, 0},        // down_1  (+ bias from d_z2)
-    {FB_DY1, 128, FB_O2, 128, 1, OUT_DIRECT, 7, 0},        // up_1
-    {FB_DY1 + 4, 128, FB_O2, 128, 1, OUT_DIRECT, 7, 128},
-    {FB_DO2, 128, FB_R2, 128, 1, OUT_DIRECT, 5, 0},        // res_2
-    {FB_DY2, 128, FB_R3, 64, 1, OUT_DIRECT, 6, 0},         // up_2
-    {FB_R2, 128, FB_DZ3, 64, 0, OUT_TRANSPOSED, 2, 0},     // down_2: D[in][out]
-    {FB_DZ1, 128, FB_XIN, 32, 0, OUT_XIN, 0, 0},           // down_0 rows 0..127 (+ bias via the ones feature)
-    {FB_DZ1 + 4, 128, FB_XIN, 32, 0, OUT_XIN, 0, 128},
-    {FB_Y1, 128, FB_DY0, 32, 0, OUT_TRANSPOSED, 8, 0},     // up_0, y1 part: D[in][out] = (d_y0^T y1)^T
-    {FB_Y1 + 4, 128, FB_DY0, 32, 0, OUT_TRANSPOSED, 8, 128},
-    {FB_R1, 128, FB_DY0, 32, 0, OUT_AUX_S, 8, 0},          // S^T = (d_y0^T r1)^T -> aux (res_1 / up_0 via fold_finish_kernel)
-    {FB_R1 + 4, 128, FB_DY0, 32, 0, OUT_AUX_S, 8, 128},
-    // M is always 128 (an M = 64 accumulator is spread over 16 lanes per TMEM quarter); the extra rows
-    // belong to the neighbouring tensors of the scratch and are ignored by the flush
-    {FB_DY0, 128, FB_XIN, 32, 0, OUT_SMALL, 3, 0},         // rows 0..31 d_y0 -> b(up_0); rows 32..63 d_o0 -> res_0, b(res_0)
-    {FB_DZ3, 128, FB_XIN, 32, 0, OUT_BIAS_ONLY, 2, 0},     // rows 0..63 d_z3 -> bias of down_2
+struct Mma {
+  int a_off, b_off, N, col;  // M = 128 rows at a_off  x  N rows at b_off  ->  TMEM columns [col, col + N)
 };
+struct StageDesc {
+  int n_load;
+  Load ld[4];
+  int n_mma;
+  Mma mma[4];
+};
+// One output block of a pass: TMEM columns [col, col + N), lane = output row
+struct OutDesc {
+  int col, N, kind, layer, row0, rows;
+};
+enum { OUT_DIRECT = 0, OUT_TRANSPOSED = 1, OUT_XIN = 2, OUT_SMALL = 3, OUT_BIAS = 4, OUT_AUX_S = 5 };
 
+constexpr int WG_A = 0, WG_B = 16384, WG_X = 49152, WG_X2 = 53248;
+constexpr int WG_RAW_BYTES = 57344;       // A | B | X | X2 as copied from the scratch
+constexpr int WG_LO = WG_RAW_BYTES;       // offset of the "lo" copy inside a stage
+constexpr int WG_STAGE_BYTES = 2 * WG_RAW_BYTES;
 constexpr int WG_STAGES = 2;
-constexpr int WG_RAW_BYTES = 16384 + 32768 + 4096;  // A | B | XIN as copied from the scratch
-constexpr int WG_LO = 53248;                         // offset of the "lo" copy inside a stage
-constexpr int WG_STAGE_BYTES = 2 * 53248;
-constexpr int WG_A = 0, WG_B = 16384, WG_X = 49152;
 constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;  // + alignment slack + barriers
 constexpr int WG_NT = 320;  // warps 0-3 split + flush, 4 MMA, 5 producer, 6-9 split
 constexpr int WG_PREFETCH = 6;  // stages of L2 prefetch lookahead
 constexpr uint64_t DESC_SW128 = 2ull << 61;  // layout type SWIZZLE_128B
+constexpr int FBB = FB_BYTES;
+
+// The stages are grouped into passes whose accumulators fit the 512 TMEM columns together; within a pass the
+// loop order is (tile, quarter) outer, stage inner; every accumulator sums over ALL tiles of the CTA and is
+// flushed once, at the end of its pass, with red.global.add.
+constexpr int N_STAGE_DESC = 7, N_OUT = 19, N_PASS = 3;
+__constant__ int c_pass_stage[N_PASS + 1] = {0, 3, 5, 7};
+__constant__ int c_pass_out[N_PASS + 1] = {0, 8, 14, 19};
+__constant__ StageDesc c_stage[N_STAGE_DESC] = {
+    // ---- pass 0: down_1 (+bias), S^T = r1^T d_y0, (d_y0^T y1)^T, down_0
+    {4, {{WG_A, FB_DZ2, 4 * FBB}, {WG_B, FB_R1, 8 * FBB}, {WG_X, FB_XIN, FBB}, {WG_X2, FB_DY0, FBB}},
+     4, {{WG_A, WG_B, 256, 0}, {WG_A, WG_X, 32, 256}, {WG_B, WG_X2, 32, 288}, {WG_B + 16384, WG_X2, 32, 320}}},
+    {2, {{WG_B, FB_Y1, 8 * FBB}, {WG_X2, FB_DY0, FBB}, {0, 0, 0}, {0, 0, 0}},
+     2, {{WG_B, WG_X2, 32, 352}, {WG_B + 16384, WG_X2, 32, 384}, {0, 0, 0, 0}, {0, 0, 0, 0}}},
+    {2, {{WG_B, FB_DZ1, 8 * FBB}, {WG_X, FB_XIN, FBB}, {0, 0, 0}, {0, 0, 0}},
+     2, {{WG_B, WG_X, 32, 416}, {WG_B + 16384, WG_X, 32, 448}, {0, 0, 0, 0}, {0, 0, 0, 0}}},
+    // ---- pass 1: up_1 (both row halves; o2 sits in the A region as the N operand), res_2
+    {3, {{WG_B, FB_DY1, 8 * FBB}, {WG_A, FB_O2, 4 * FBB}, {WG_X, FB_XIN, FBB}, {0, 0, 0}},
+     4, {{WG_B, WG_A, 128, 0}, {WG_B, WG_X, 32, 128}, {WG_B + 16384, WG_A, 128, 160}, {WG_B + 16384, WG_X, 32, 288}}},
+    {3, {{WG_A, FB_DO2, 4 * FBB}, {WG_B, FB_R2, 4 * FBB}, {WG_X, FB_XIN, FBB}, {0, 0, 0}},
+     2, {{WG_A, WG_B, 128, 320}, {WG_A, WG_X, 32, 448}, {0, 0, 0, 0}, {0, 0, 0, 0}}},
+    // ---- pass 2: up_2, down_2 (D[in][out]) + its bias, and the d-sized layers
+    {3, {{WG_A, FB_DY2, 4 * FBB}, {WG_B, FB_R3, 2 * FBB}, {WG_X, FB_XIN, FBB}, {0, 0, 0}},
+     2, {{WG_A, WG_B, 64, 0}, {WG_A, WG_X, 32, 64}, {0, 0, 0, 0}, {0, 0, 0, 0}}},
+    // M is always 128 (an M = 64 accumulator is spread over 16 lanes per TMEM quarter): the d_z3 and d_y0 row
+    // blocks are loaded with the neighbouring tensors of the scratch, whose rows the flush ignores
+    {4, {{WG_A, FB_R2, 4 * FBB}, {WG_B, FB_DZ3, 4 * FBB}, {WG_B + 16384, FB_DY0, 4 * FBB}, {WG_X, FB_XIN, FBB}},
+     3, {{WG_A, WG_B, 64, 96}, {WG_B, WG_X, 32, 160}, {WG_B + 16384, WG_X, 32, 192}, {0, 0, 0, 0}}},
+};
+__constant__ OutDesc c_out[N_OUT] = {
+    {0, 256, OUT_DIRECT, 1, 0, 128},    {256, 32, OUT_BIAS, 1, 0, 128},        // down_1
+    {288, 32, OUT_AUX_S, 8, 0, 128},    {320, 32, OUT_AUX_S, 8, 128, 128},     // S^T -> aux (res_1 / up_0 via fold_finish_kernel)
+    {352, 32, OUT_TRANSPOSED, 8, 0, 128}, {384, 32, OUT_TRANSPOSED, 8, 128, 128},  // up_0, y1 part
+    {416, 32, OUT_XIN, 0, 0, 128},      {448, 32, OUT_XIN, 0, 128, 128},       // down_0 (+ bias via the ones feature)
+    {0, 128, OUT_DIRECT, 7, 0, 128},    {128, 32, OUT_BIAS, 7, 0, 128},        // up_1 rows 0..127
+    {160, 128, OUT_DIRECT, 7, 128, 128}, {288, 32, OUT_BIAS, 7, 128, 128},     // up_1 rows 128..255
+    {320, 128, OUT_DIRECT, 5, 0, 128},  {448, 32, OUT_BIAS, 5, 0, 128},        // res_2
+    {0, 64, OUT_DIRECT, 6, 0, 128},     {64, 32, OUT_BIAS, 6, 0, 128},         // up_2
+    {96, 64, OUT_TRANSPOSED, 2, 0, 128},                                       // down_2
+    {160, 32, OUT_BIAS, 2, 0, 64},                                             // bias of down_2 (rows = d_z3 features)
+    {192, 32, OUT_SMALL, 3, 0, 64},     // rows 0..31 d_y0 -> b(up_0), aux sb; rows 32..63 d_o0 -> res_0, b(res_0)
+};
 
 // K-major operand, 128-byte rows (32 points per feature), 8-row swizzle atoms of 1 KB stacked along the features
 __device__ __forceinline__ uint64_t mn_desc(uint32_t saddr) { return smem_desc(saddr, 16, 1024) | DESC_SW128; }
@@ -73,7 +111,7 @@ __device__ __forceinline__ void red_add(float* p, float v) {
 __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char* __restrict__ scratch, int n_tiles,
                                                             int d, float* __restrict__ grad, float* __restrict__ aux) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // stage bases must be 512-byte aligned in the shared window: the operand swizzle uses address bits 7-8
+  // stage bases must be 1 KB aligned in the shared window: the operand swizzle uses address bits 7-9
   unsigned char* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
   uint64_t* full = bars;                  // [WG_STAGES] bulk copies landed
@@ -103,54 +141,62 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
   const GradOffTc go = grad_offsets_tc(d);
 
   if (warp == 5) {
-    // ===================================================== producer: one stage = (layer block, tile, quarter)
+    // ===================================================== producer: one pipeline stage = (stage desc, tile, quarter)
     // Only two stages fit in shared memory (raw + lo copies), far too little to cover the HBM latency, so
     // the producer runs an L2 prefetch (cp.async.bulk.prefetch.L2) WG_PREFETCH stages ahead of the copies.
     if (elect_one()) {
       struct Cursor {
-        int l, ti, q;  // layer block, index into this CTA's tiles, quarter
+        int pass, ti, q, l;  // pass, index into this CTA's tiles, quarter, stage desc of the pass
       };
       auto advance = [&](Cursor& c) {
-        if (++c.q == 4) {
-          c.q = 0;
-          if (++c.ti == my_tiles) {
-            c.ti = 0;
-            ++c.l;
+        if (++c.l == c_pass_stage[c.pass + 1]) {
+          c.l = c_pass_stage[c.pass];
+          if (++c.q == 4) {
+            c.q = 0;
+            if (++c.ti == my_tiles) {
+              c.ti = 0;
+              ++c.pass;
+              c.l = c.pass < N_PASS ? c_pass_stage[c.pass] : 0;
+            }
           }
         }
       };
       auto prefetch = [&](const Cursor& c) {
-        if (c.l >= N_LB) return;
-        const LayerBlock lb = c_lb[c.l];
+        if (c.pass >= N_PASS) return;
         const unsigned char* qb = scratch + (size_t)(blockIdx.x + c.ti * gridDim.x) * TILE_BYTES + (size_t)c.q * QUARTER_BYTES;
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(qb + (size_t)lb.a_fb * FB_BYTES), "r"(lb.M * 128) : "memory");
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(qb + (size_t)lb.b_fb * FB_BYTES), "r"(lb.N * 128) : "memory");
-        if (lb.with_x)
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(qb + (size_t)FB_XIN * FB_BYTES), "r"(FB_BYTES) : "memory");
+        const int nl = c_stage[c.l].n_load;
+        for (int j = 0; j < nl; ++j) {
+          const Load ld = c_stage[c.l].ld[j];
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(qb + (size_t)ld.fb * FB_BYTES), "r"(ld.bytes) : "memory");
+        }
       };
-      Cursor ahead{0, 0, 0};
+      Cursor ahead{0, 0, 0, 0};
       if (my_tiles > 0)
         for (int i = 0; i < WG_PREFETCH; ++i) {
           prefetch(ahead);
           advance(ahead);
         }
       uint32_t it = 0;
-      for (int l = 0; l < N_LB && my_tiles > 0; ++l) {
-        const LayerBlock lb = c_lb[l];
-        const uint32_t a_bytes = (uint32_t)lb.M * 128u, b_bytes = (uint32_t)lb.N * 128u;
+      for (int pass = 0; pass < N_PASS && my_tiles > 0; ++pass) {
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
           const unsigned char* tile = scratch + (size_t)t * TILE_BYTES;
-          for (int q = 0; q < 4; ++q, ++it) {
-            prefetch(ahead);
-            advance(ahead);
-            const uint32_t s = it % WG_STAGES;
-            mbar_wait(&empty[s], ((it / WG_STAGES) & 1) ^ 1);
-            unsigned char* st = smem + s * WG_STAGE_BYTES;
+          for (int q = 0; q < 4; ++q) {
             const unsigned char* qb = tile + (size_t)q * QUARTER_BYTES;
-            mbar_expect_tx(&full[s], a_bytes + b_bytes + (lb.with_x ? FB_BYTES : 0));
-            bulk_g2s(st + WG_A, qb + (size_t)lb.a_fb * FB_BYTES, a_bytes, &full[s]);
-            bulk_g2s(st + WG_B, qb + (size_t)lb.b_fb * FB_BYTES, b_bytes, &full[s]);
-            if (lb.with_x) bulk_g2s(st + WG_X, qb + (size_t)FB_XIN * FB_BYTES, FB_BYTES, &full[s]);
+            for (int l = c_pass_stage[pass]; l < c_pass_stage[pass + 1]; ++l, ++it) {
+              prefetch(ahead);
+              advance(ahead);
+              const uint32_t s = it % WG_STAGES;
+              mbar_wait(&empty[s], ((it / WG_STAGES) & 1) ^ 1);
+              unsigned char* st = smem + s * WG_STAGE_BYTES;
+              const int nl = c_stage[l].n_load;
+              uint32_t total = 0;
+              for (int j = 0; j < nl; ++j) total += (uint32_t)c_stage[l].ld[j].bytes;
+              mbar_expect_tx(&full[s], total);
+              for (int j = 0; j < nl; ++j) {
+                const Load ld = c_stage[l].ld[j];
+                bulk_g2s(st + ld.dst, qb + (size_t)ld.fb * FB_BYTES, (uint32_t)ld.bytes, &full[s]);
+              }
+            }
           }
         }
       }
@@ -159,38 +205,36 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
   } else if (warp == 4) {
     // ===================================================== MMA issue
     uint32_t it = 0;
-    for (int l = 0; l < N_LB; ++l) {
-      const LayerBlock lb = c_lb[l];
+    for (int pass = 0; pass < N_PASS; ++pass) {
       if (my_tiles == 0) break;
-      mbar_wait(acc_empty, (l & 1) ^ 1);  // the flush warps have drained the previous block
+      mbar_wait(acc_empty, (pass & 1) ^ 1);  // the flush warps have drained the previous pass
       fence_after_sync();
-      const uint32_t idesc = idesc_tf32(lb.M, lb.N, 0, 0);
-      const uint32_t idesc_x = idesc_tf32(lb.M, 32, 0, 0);
-      uint32_t first = 1;
-      for (int i = 0; i < my_tiles * 4; ++i, ++it) {
-        const uint32_t s = it % WG_STAGES;
-        mbar_wait(&split[s], (it / WG_STAGES) & 1);
-        fence_after_sync();
-        const uint32_t st = smem_addr(smem + s * WG_STAGE_BYTES);
-        if (elect_one()) {
+      for (int i = 0; i < my_tiles * 4; ++i) {
+        for (int l = c_pass_stage[pass]; l < c_pass_stage[pass + 1]; ++l, ++it) {
+          const uint32_t first = i == 0 ? 1u : 0u;
+          const uint32_t s = it % WG_STAGES;
+          mbar_wait(&split[s], (it / WG_STAGES) & 1);
+          fence_after_sync();
+          const uint32_t st = smem_addr(smem + s * WG_STAGE_BYTES);
+          if (elect_one()) {
+            const int nm = c_stage[l].n_mma;
+            for (int j = 0; j < nm; ++j) {
+              const Mma m = c_stage[l].mma[j];
+              const uint32_t idesc = idesc_tf32(128, m.N, 0, 0);
+              const uint32_t dcol = tm + (uint32_t)m.col;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = mn_desc(st + WG_A + ks * 32), al = mn_desc(st + WG_LO + WG_A + ks * 32);
-            const uint64_t bd = mn_desc(st + WG_B + ks * 32), bl = mn_desc(st + WG_LO + WG_B + ks * 32);
-            mma_ss(tm, ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
-            mma_ss(tm, al, bd, idesc, 1u);
-            mma_ss(tm, ad, bl, idesc, 1u);
-            if (lb.with_x) {
-              const uint64_t xd = mn_desc(st + WG_X + ks * 32), xl = mn_desc(st + WG_LO + WG_X + ks * 32);
-              mma_ss(tm + 256, ad, xd, idesc_x, (first && ks == 0) ? 0u : 1u);
-              mma_ss(tm + 256, al, xd, idesc_x, 1u);
-              mma_ss(tm + 256, ad, xl, idesc_x, 1u);
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t ad = mn_desc(st + m.a_off + ks * 32), al = mn_desc(st + WG_LO + m.a_off + ks * 32);
+                const uint64_t bd = mn_desc(st + m.b_off + ks * 32), bl = mn_desc(st + WG_LO + m.b_off + ks * 32);
+                mma_ss(dcol, ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
+                mma_ss(dcol, al, bd, idesc, 1u);
+                mma_ss(dcol, ad, bl, idesc, 1u);
+              }
             }
+            commit(&empty[s]);
           }
-          commit(&empty[s]);
+          __syncwarp();
         }
-        __syncwarp();
-        first = 0;
       }
       if (elect_one()) commit(acc_full);
       __syncwarp();
@@ -202,46 +246,50 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
     const uint32_t lane_t = tm + ((uint32_t)((warp & 3) * 32) << 16);
     const int r = tid & 127;
     uint32_t it = 0;
-    for (int l = 0; l < N_LB; ++l) {
-      const LayerBlock lb = c_lb[l];
+    for (int pass = 0; pass < N_PASS; ++pass) {
       if (my_tiles == 0) break;
-      // ---- split every stage of this layer block: lo = x - trunc_tf32(x)
-      const int a_f4 = lb.M * 8, b_f4 = lb.N * 8;  // float4 counts of the A / B parts (32 points x 4 B per feature)
-      for (int i = 0; i < my_tiles * 4; ++i, ++it) {
-        const uint32_t s = it % WG_STAGES;
-        mbar_wait(&full[s], (it / WG_STAGES) & 1);
-        float4* raw = reinterpret_cast<float4*>(smem + s * WG_STAGE_BYTES);
-        float4* lo = reinterpret_cast<float4*>(smem + s * WG_STAGE_BYTES + WG_LO);
-        auto split_range = [&](int f4_begin, int n_f4) {
-          for (int j = sid; j < n_f4; j += 256) {
-            const float4 x = raw[f4_begin + j];
-            float4 hi, y;
-            hi.x = tf32_rn(x.x); hi.y = tf32_rn(x.y); hi.z = tf32_rn(x.z); hi.w = tf32_rn(x.w);
-            y.x = x.x - hi.x; y.y = x.y - hi.y; y.z = x.z - hi.z; y.w = x.w - hi.w;
-            raw[f4_begin + j] = hi;  // round-to-nearest split (unbiased; the MMA would truncate)
-            lo[f4_begin + j] = y;
+      // ---- split every stage of this pass: hi = rn_tf32(x) in place, lo = x - hi (second copy)
+      for (int i = 0; i < my_tiles * 4; ++i)
+        for (int l = c_pass_stage[pass]; l < c_pass_stage[pass + 1]; ++l, ++it) {
+          const uint32_t s = it % WG_STAGES;
+          mbar_wait(&full[s], (it / WG_STAGES) & 1);
+          float4* raw = reinterpret_cast<float4*>(smem + s * WG_STAGE_BYTES);
+          float4* lo = reinterpret_cast<float4*>(smem + s * WG_STAGE_BYTES + WG_LO);
+          const int nl = c_stage[l].n_load;
+          for (int jl = 0; jl < nl; ++jl) {
+            const int f4_begin = c_stage[l].ld[jl].dst / 16, n_f4 = c_stage[l].ld[jl].bytes / 16;
+            for (int j = sid; j < n_f4; j += 256) {
+              const float4 x = raw[f4_begin + j];
+              float4 hi, y;
+              hi.x = tf32_rn(x.x); hi.y = tf32_rn(x.y); hi.z = tf32_rn(x.z); hi.w = tf32_rn(x.w);
+              y.x = x.x - hi.x; y.y = x.y - hi.y; y.z = x.z - hi.z; y.w = x.w - hi.w;
+              raw[f4_begin + j] = hi;  // round-to-nearest split (unbiased; the MMA would truncate)
+              lo[f4_begin + j] = y;
+            }
           }
-        };
-        split_range(WG_A / 16, a_f4);
-        split_range(WG_B / 16, b_f4);
-        if (lb.with_x) split_range(WG_X / 16, FB_BYTES / 16);
-        fence_async_smem();
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&split[s]);
-      }
+          fence_async_smem();
+          __syncwarp();
+          if ((tid & 31) == 0) mbar_arrive(&split[s]);
+        }
       if (!flusher) continue;
-      mbar_wait(acc_full, l & 1);
+      mbar_wait(acc_full, pass & 1);
       fence_after_sync();
-      const bool row_ok = true;
-      const int row = lb.row0 + r;
-      {
-        for (int c0 = 0; c0 < lb.N; c0 += 16) {
+      for (int o = c_pass_out[pass]; o < c_pass_out[pass + 1]; ++o) {
+        const OutDesc od = c_out[o];
+        const int row = od.row0 + r;
+        if (od.kind == OUT_BIAS) {  // column ONES_FEATURE of (rows x XIN)
           float v[16];
-          tmem_ld16(lane_t + c0, reinterpret_cast<uint32_t*>(v));
+          tmem_ld16(lane_t + od.col + 16, reinterpret_cast<uint32_t*>(v));
           tmem_wait_ld();
-          if (!row_ok) continue;
-          if (lb.kind == OUT_DIRECT) {
-            float* dst = grad + go.w[lb.layer] + (size_t)row * lb.N + c0;
+          if (r < od.rows) red_add(grad + go.b[od.layer] + row, v[ONES_FEATURE - 16]);
+          continue;
+        }
+        for (int c0 = 0; c0 < od.N; c0 += 16) {
+          float v[16];
+          tmem_ld16(lane_t + od.col + c0, reinterpret_cast<uint32_t*>(v));
+          tmem_wait_ld();
+          if (od.kind == OUT_DIRECT) {
+            float* dst = grad + go.w[od.layer] + (size_t)row * od.N + c0;
             if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
               for (int j = 0; j < 16; j += 4)
@@ -252,18 +300,18 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
 #pragma unroll
               for (int j = 0; j < 16; ++j) red_add(dst + j, v[j]);
             }
-          } else if (lb.kind == OUT_TRANSPOSED) {
+          } else if (od.kind == OUT_TRANSPOSED) {
             // D[in = row][out = c]: weight (layer) is [out][in_total]; up_0: out < d, in_total = 256; down_2: in_total = 128
-            const int in_total = lb.layer == 8 ? 256 : 128;
-            const int n_out = lb.layer == 8 ? d : 64;
+            const int in_total = od.layer == 8 ? 256 : 128;
+            const int n_out = od.layer == 8 ? d : 64;
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (c0 + j < n_out) red_add(grad + go.w[lb.layer] + (size_t)(c0 + j) * in_total + row, v[j]);
-          } else if (lb.kind == OUT_AUX_S) {
+              if (c0 + j < n_out) red_add(grad + go.w[od.layer] + (size_t)(c0 + j) * in_total + row, v[j]);
+          } else if (od.kind == OUT_AUX_S) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
               if (c0 + j < d) red_add(aux + AUX_S + (c0 + j) * 256 + row, v[j]);
-          } else if (lb.kind == OUT_XIN) {
+          } else if (od.kind == OUT_XIN) {
             // down_0: D[out = row][k]: k <= d -> weight, k = ONES_FEATURE -> bias
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -271,8 +319,7 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
               if (k <= d) red_add(grad + go.w[0] + (size_t)row * (d + 1) + k, v[j]);
               if (k == ONES_FEATURE) red_add(grad + go.b[0] + row, v[j]);
             }
-          } else if (lb.kind == OUT_SMALL) {
-            // rows 0..31: d_y0[j]; rows 32..63: d_o0[j]
+          } else {  // OUT_SMALL: rows 0..31: d_y0[j]; rows 32..63: d_o0[j]
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int k = c0 + j;
@@ -286,17 +333,7 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
                 if (k == ONES_FEATURE) red_add(grad + go.b[3] + (r - 32), v[j]);
               }
             }
-          } else {  // OUT_BIAS_ONLY (down_2: rows = d_z3 features)
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (r < 64 && c0 + j == ONES_FEATURE) red_add(grad + go.b[2] + r, v[j]);
           }
-        }
-        if (lb.with_x) {  // bias of the layer: column ONES_FEATURE of A x XIN
-          float v[16];
-          tmem_ld16(lane_t + 256 + 16, reinterpret_cast<uint32_t*>(v));
-          tmem_wait_ld();
-          if (row_ok) red_add(grad + go.b[lb.layer] + row, v[ONES_FEATURE - 16]);
         }
       }
       fence_before_sync();
