@@ -182,24 +182,38 @@ __global__ void __launch_bounds__(k3::NT, 1)
         const bool live = m < B;
         const uint32_t ph = g & 1;
         unsigned char* sq = scratch + (size_t)lt * TILE_BYTES + (size_t)q * QUARTER_BYTES;  // this warp's quarter
-        uint32_t m_r1[8], m_r2[2], m_r3 = 0, m_y2[2], m_y1[8];
+        // ReLU masks of this thread's columns, packed so that the rolled loops below need no indexed registers
+        // (the E program is executed once per tile and must stay small: instruction fetch, not issue, limits it)
+        uint64_t m_r1a = 0, m_r1b = 0, m_y1a = 0, m_y1b = 0, m_r2 = 0, m_y2 = 0;
+        uint32_t m_r3 = 0;
         float x[KIN];
         K3P_RESET;
         K3P_MARK;
 
-        // chunk producer: v(16 cols) = f(accumulator columns) -> shared-memory A chunk; `fn` post-processes the 16 values
+        // chunk producer: v(16 cols) = f(accumulator columns) -> shared-memory A chunk; `fn` post-processes the 16
+        // values.  The TMEM load of chunk c+1 is in flight while chunk c is processed (a tcgen05.ld that competes
+        // with running MMAs takes ~450 cycles), and the chunk buffer is waited for last: nothing before the
+        // shared-memory stores depends on it.
         auto chunks = [&](uint32_t src_col, auto&& fn) {
-          for (int c = 0; c < 8; ++c) {
+          auto body = [&](int c, float* v) {
+            fn(c, v);
             const int b = cu & 1;
             mbar_wait(&bars[CH_EMPTY + b], ((cu >> 1) & 1) ^ 1);
-            float v[16];
-            tmem_ld16(lane_t + src_col + 32 * c + 16 * h, reinterpret_cast<uint32_t*>(v));
-            tmem_wait_ld();
-            fn(c, v);
             store_chunk16(smem + SM_CHUNK + b * CHUNK_BYTES, p, 4 * h, v);
             fence_async_smem();
             warp_arrive(&bars[CH_FULL + b]);
             ++cu;
+          };
+          float va[16], vb[16];
+          tmem_ld16(lane_t + src_col + 16 * h, reinterpret_cast<uint32_t*>(va));
+#pragma unroll 1
+          for (int c = 0; c < 8; c += 2) {
+            tmem_wait_ld();
+            tmem_ld16(lane_t + src_col + 32 * (c + 1) + 16 * h, reinterpret_cast<uint32_t*>(vb));
+            body(c, va);
+            tmem_wait_ld();
+            if (c + 2 < 8) tmem_ld16(lane_t + src_col + 32 * (c + 2) + 16 * h, reinterpret_cast<uint32_t*>(va));
+            body(c + 1, vb);
           }
         };
 
@@ -239,7 +253,9 @@ __global__ void __launch_bounds__(k3::NT, 1)
         fence_after_sync();
         chunks(C_SA, [&](int c, float* v) {
           bias_relu16(v, sm_small + so.b_d0 + 32 * c + 16 * h);
-          m_r1[c] = positive_bits<16>(v);
+          const uint64_t bits = (uint64_t)positive_bits<16>(v) << (16 * (c & 3));
+          if (c < 4) m_r1a |= bits;
+          else m_r1b |= bits;
           store_fb16(sq + (FB_R1 + c) * FB_BYTES, ro, 16 * h, v);
         });
         // ---- F2: r2
@@ -256,14 +272,14 @@ __global__ void __launch_bounds__(k3::NT, 1)
 #pragma unroll
           for (int j = 0; j < KIN; ++j) au[j] = yp[j];
         }
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < 2; ++i) {
           const int cb = 2 * h + i;
           float v[32];
           tmem_ld32(lane_t + C_D1 + 32 * cb, reinterpret_cast<uint32_t*>(v));
           tmem_wait_ld();
           bias_relu32(v, sm_small + so.b_d1 + 32 * cb);
-          m_r2[i] = positive_bits<32>(v);
+          m_r2 |= (uint64_t)positive_bits<32>(v) << (32 * i);
           store_split32(lane_t + C_SA + 32 * cb, lane_t + C_SA + 128 + 32 * cb, v);
           store_fb32(sq + (FB_R2 + cb) * FB_BYTES, ro, v);
         }
@@ -292,14 +308,14 @@ __global__ void __launch_bounds__(k3::NT, 1)
         mbar_wait(&bars[D3A_FULL], ph);
         K3P_MARK;
         fence_after_sync();
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < 2; ++i) {
           const int cb = 2 * h + i;
           float v[32];
           tmem_ld32(lane_t + C_D3 + 32 * cb, reinterpret_cast<uint32_t*>(v));
           tmem_wait_ld();
           bias_relu32(v, sm_small + so.b_u2 + 32 * cb);
-          m_y2[i] = positive_bits<32>(v);
+          m_y2 |= (uint64_t)positive_bits<32>(v) << (32 * i);
           tmem_st32(lane_t + C_D3 + 32 * cb, reinterpret_cast<const uint32_t*>(v));
         }
         tmem_wait_st();
@@ -310,7 +326,7 @@ __global__ void __launch_bounds__(k3::NT, 1)
         mbar_wait(&bars[D3B_FULL], ph);
         K3P_MARK;
         fence_after_sync();
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < 2; ++i) {
           const int cb = 2 * h + i;
           float v[32];
@@ -330,7 +346,9 @@ __global__ void __launch_bounds__(k3::NT, 1)
         fence_after_sync();
         chunks(C_D4, [&](int c, float* v) {
           bias_relu16(v, sm_small + so.b_u1 + 32 * c + 16 * h);
-          m_y1[c] = positive_bits<16>(v);
+          const uint64_t bits = (uint64_t)positive_bits<16>(v) << (16 * (c & 3));
+          if (c < 4) m_y1a |= bits;
+          else m_y1b |= bits;
           store_fb16(sq + (FB_Y1 + c) * FB_BYTES, ro, 16 * h, v);
         });
         // ---- F8 (owners): y0 = W_u0 y1 (TMEM [0,NY)) + Wc r1 (registers) + bc
@@ -423,7 +441,7 @@ __global__ void __launch_bounds__(k3::NT, 1)
         K3P_MARK;
         fence_after_sync();
         chunks(C_SA, [&](int c, float* v) {
-          apply_bits<16>(v, m_y1[c]);
+          apply_bits<16>(v, (uint32_t)((c < 4 ? m_y1a : m_y1b) >> (16 * (c & 3))));
           store_fb16(sq + (FB_DY1 + c) * FB_BYTES, ro, 16 * h, v);
         });
         // ---- B2: d_o2 -> A operand; d_o2, d_y2 -> scratch
@@ -431,7 +449,7 @@ __global__ void __launch_bounds__(k3::NT, 1)
         mbar_wait(&bars[BDO2_FULL], ph);
         K3P_MARK;
         fence_after_sync();
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < 2; ++i) {
           const int cb = 2 * h + i;
           float v[32];
@@ -439,7 +457,7 @@ __global__ void __launch_bounds__(k3::NT, 1)
           tmem_wait_ld();
           store_split32(lane_t + C_SA + 32 * cb, lane_t + C_SA + 128 + 32 * cb, v);
           store_fb32(sq + (FB_DO2 + cb) * FB_BYTES, ro, v);
-          apply_bits<32>(v, m_y2[i]);
+          apply_bits<32>(v, (uint32_t)(m_y2 >> (32 * i)));
           store_fb32(sq + (FB_DY2 + cb) * FB_BYTES, ro, v);
         }
         tmem_wait_st();
@@ -450,13 +468,13 @@ __global__ void __launch_bounds__(k3::NT, 1)
         mbar_wait(&bars[BR2A_FULL], ph);
         K3P_MARK;
         fence_after_sync();
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < 2; ++i) {
           const int cb = 2 * h + i;
           float v[32];
           tmem_ld32(lane_t + C_DO2 + 32 * cb, reinterpret_cast<uint32_t*>(v));
           tmem_wait_ld();
-          apply_bits<32>(v, m_y2[i]);
+          apply_bits<32>(v, (uint32_t)(m_y2 >> (32 * i)));
           store_split32(lane_t + C_SA + 32 * cb, lane_t + C_SA + 128 + 32 * cb, v);
         }
         tmem_wait_st();
@@ -483,13 +501,13 @@ __global__ void __launch_bounds__(k3::NT, 1)
         mbar_wait(&bars[BR2B_FULL], ph);
         K3P_MARK;
         fence_after_sync();
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < 2; ++i) {
           const int cb = 2 * h + i;
           float v[32];
           tmem_ld32(lane_t + C_DR2 + 32 * cb, reinterpret_cast<uint32_t*>(v));
           tmem_wait_ld();
-          apply_bits<32>(v, m_r2[i]);
+          apply_bits<32>(v, (uint32_t)(m_r2 >> (32 * i)));
           store_split32(lane_t + C_SA + 32 * cb, lane_t + C_SA + 128 + 32 * cb, v);
           store_fb32(sq + (FB_DZ2 + cb) * FB_BYTES, ro, v);
         }
@@ -501,13 +519,22 @@ __global__ void __launch_bounds__(k3::NT, 1)
         mbar_wait(&bars[BD1B_FULL], ph);
         K3P_MARK;
         fence_after_sync();
+        {
+          auto body = [&](int c, float* v) {
+            apply_bits<16>(v, (uint32_t)((c < 4 ? m_r1a : m_r1b) >> (16 * (c & 3))));
+            store_fb16(sq + (FB_DZ1 + c) * FB_BYTES, ro, 16 * h, v);
+          };
+          float va[16], vb[16];
+          tmem_ld16(lane_t + C_DR1 + 16 * h, reinterpret_cast<uint32_t*>(va));
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-          float v[16];
-          tmem_ld16(lane_t + C_DR1 + 32 * c + 16 * h, reinterpret_cast<uint32_t*>(v));
-          tmem_wait_ld();
-          apply_bits<16>(v, m_r1[c]);
-          store_fb16(sq + (FB_DZ1 + c) * FB_BYTES, ro, 16 * h, v);
+          for (int c = 0; c < 8; c += 2) {
+            tmem_wait_ld();
+            tmem_ld16(lane_t + C_DR1 + 32 * (c + 1) + 16 * h, reinterpret_cast<uint32_t*>(vb));
+            body(c, va);
+            tmem_wait_ld();
+            if (c + 2 < 8) tmem_ld16(lane_t + C_DR1 + 32 * (c + 2) + 16 * h, reinterpret_cast<uint32_t*>(va));
+            body(c + 1, vb);
+          }
         }
         fence_before_sync();  // TMEM reads done before the next tile's MMAs (ordered through XIN_FULL / e_sync)
         K3P_MARK;

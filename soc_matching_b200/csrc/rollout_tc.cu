@@ -201,19 +201,29 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
 #pragma unroll
     for (int j = 0; j < KIN; ++j) kap[j] = (h == 0 && diag && j < d) ? __ldg(a.st.kappa + j) : 0.f;
 
-    // relu(acc + bias) of a 256-wide accumulator -> 8 shared-memory A chunks, 16 features per half
+    // relu(acc + bias) of a 256-wide accumulator -> 8 shared-memory A chunks, 16 features per half.
+    // The TMEM load of chunk c+1 is in flight while chunk c is processed (a tcgen05.ld that competes with
+    // running MMAs takes ~450 cycles) and the chunk buffer is waited for last.
     auto gen_chunks = [&](uint32_t src_col, int bias_off) {
-      for (int c = 0; c < 8; ++c) {
+      auto body = [&](int c, float* v) {
+        bias_relu16(v, sm_small + bias_off + 32 * c + 16 * h);
         const int b = cu & 1;
         mbar_wait(&bars[CH_EMPTY + b], ((cu >> 1) & 1) ^ 1);
-        float v[16];
-        tmem_ld16(lane_t + src_col + 32 * c + 16 * h, reinterpret_cast<uint32_t*>(v));
-        tmem_wait_ld();
-        bias_relu16(v, sm_small + bias_off + 32 * c + 16 * h);
         store_chunk16(smem + SM_CHUNK + b * CHUNK_BYTES, p, 4 * h, v);
         fence_async_smem();
         warp_arrive(&bars[CH_FULL + b]);
         ++cu;
+      };
+      float va[16], vb[16];
+      tmem_ld16(lane_t + src_col + 16 * h, reinterpret_cast<uint32_t*>(va));
+#pragma unroll 1
+      for (int c = 0; c < 8; c += 2) {
+        tmem_wait_ld();
+        tmem_ld16(lane_t + src_col + 32 * (c + 1) + 16 * h, reinterpret_cast<uint32_t*>(vb));
+        body(c, va);
+        tmem_wait_ld();
+        if (c + 2 < 8) tmem_ld16(lane_t + src_col + 32 * (c + 2) + 16 * h, reinterpret_cast<uint32_t*>(va));
+        body(c + 1, vb);
       }
     };
 
