@@ -43,18 +43,11 @@ t3 = timeit(k3)
 n_tiles = (K + 1) * (B // 128)
 print(f"{os.environ.get('SOCM_B200_LIB', 'default')}: B={B} K3 {t3:.2f} ms ({n_tiles} tiles, {t3 * 1e3 / (n_tiles / 148):.1f} us/tile/SM)", end="")
 if os.environ.get("AB_K1", "1") == "1":
-    from helpers import make_product_sde
-    try:
-        s = sde_mod.DoubleWell(d=d, device=DEV) if hasattr(sde_mod, "DoubleWell") else None
-    except Exception as e:
-        s = None
-    if s is not None:
-        try:
-            s.nabla_V = unet
-            x0 = torch.zeros(65536, d, device=DEV)
-            fn = lambda: simulate.stochastic_trajectories(s, x0, ts, 1.0)
-            t1 = timeit(fn, 3)
-            print(f"  K1 {t1:.2f} ms for 65536 paths", end="")
-        except Exception as e:
-            print("  K1 skipped:", repr(e)[:100], end="")
+    from helpers import make_product_sde, random_setting, seeded_mnet
+    stg = random_setting("double_well", d, seed=3)
+    gam = {"gamma": torch.tensor([6.0]), "gamma2": torch.tensor([1.0]), "gamma3": torch.tensor([1.0])}
+    sde = make_product_sde(stg, seeded_unet(d, [256, 128, 64], 5), seeded_mnet(d, [128, 128], 6), gam, [256, 128, 64], [128, 128], DEV)
+    x0 = torch.zeros(148 * 128 * 2, d, device=DEV)
+    t1 = timeit(lambda: simulate.rollout(sde, x0, ts, 1.0, seed=1), 3)
+    print(f"  K1 {t1:.2f} ms for {x0.shape[0]} paths x {K} steps", end="")
 print()

@@ -59,7 +59,8 @@ enum Bar {
 constexpr int NT = 320, NE = 256;
 constexpr uint32_t C_SA = 0, C_D1 = 256, C_D2 = 256, C_D3 = 256, C_R3 = 384, C_D4 = 256;
 constexpr uint32_t C_DO2 = 256, C_DR2 = 384, C_DR3 = 256, C_DR1 = 256;
-constexpr uint32_t C_Y0P = 384, C_Y0 = 0;  // folded last layer: Wc r1 (next to down_1) and W_u0 y1 (after up_1)
+constexpr uint32_t C_Y0P = 384, C_Y0 = 0;
+static_assert(C_Y0P == C_D1 + H1, "Wc r1 must sit right behind the down_1 accumulator (joint MMA)");  // folded last layer: Wc r1 (next to down_1) and W_u0 y1 (after up_1)
 }  // namespace k3
 
 __host__ __device__ inline int loss_tc_smem_bytes(int d) {
@@ -591,8 +592,9 @@ __global__ void __launch_bounds__(k3::NT, 1)
         fence_after_sync();
         const uint32_t wb = wait_w();
         if (elect_one()) {
-          issue_block_ss<H1, 32>(tm + d_col, chunk_s + b * CHUNK_BYTES, CHUNK_HALF, wb, c == 0);
-          if (with_wc) issue_block_ss<NY, 32>(tm + C_Y0P, chunk_s + b * CHUNK_BYTES, CHUNK_HALF, wb + MAIN_BYTES, c == 0);
+          // forward: down_1 and Wc r1 in one MMA (N = H1 + NY: columns [C_D1, C_D1 + H1) and [C_Y0P, C_Y0P + NY))
+          if (with_wc) issue_block_ss<H1 + NY, 32>(tm + d_col, chunk_s + b * CHUNK_BYTES, CHUNK_HALF, wb, c == 0);
+          else issue_block_ss<H1, 32>(tm + d_col, chunk_s + b * CHUNK_BYTES, CHUNK_HALF, wb, c == 0);
           commit(&bars[CH_EMPTY + b]);
         }
         __syncwarp();

@@ -52,14 +52,14 @@ __global__ void pack_tc_kernel(socm_unet net, const float* __restrict__ wc, unsi
     const SlotDesc sd = pi.sd;
     const float* W = sd.layer == WC_LAYER ? wc : net.w[sd.layer];
     unsigned char* base = tape + (size_t)(pi.slot + (it < n_fi ? 0 : fwd_slots(d))) * SLOT_BYTES + pi.byte_off;
-    const int slab = sd.N * sd.Kc * 4;
+    const int slab = (sd.slab_n ? sd.slab_n : sd.N) * sd.Kc * 4;
     for (int i = tid; i < sd.N * sd.Kc; i += nth) {
       const int n = i / sd.Kc, k = i - n * sd.Kc;
       float w = 0.f;
       if (sd.k0 + k < sd.klim && sd.n0 + n < sd.nlim)
         w = sd.transposed ? W[(size_t)(sd.k0 + k) * sd.ktot + sd.n0 + n] : W[(size_t)(sd.n0 + n) * sd.ktot + sd.k0 + k];
       const float hi = tf32_rn(w);
-      const int off = wslab_off(n, k, sd.Kc);
+      const int off = wslab_off(sd.slab_row + n, k, sd.Kc);
       *reinterpret_cast<float*>(base + off) = hi;
       *reinterpret_cast<float*>(base + slab + off) = w - hi;
     }
@@ -112,6 +112,7 @@ constexpr uint32_t C_SA = 0, C_D1 = 256, C_D2 = 256, C_D3 = 256, C_R3 = 384, C_D
 // folded last layer (unet_tc.cuh): C_Y0P = Wc r1, accumulated next to down_1 and read out before r3 is
 // written there; C_Y0 = W_u0 y1, accumulated over the y1 chunks once up_1 has consumed o2.
 constexpr uint32_t C_Y0P = 384, C_Y0 = 0;
+static_assert(C_Y0P == C_D1 + H1, "Wc r1 must sit right behind the down_1 accumulator (joint MMA)");
 
 
 // eps[0..d) for (path m, step k) into registers: injected or Philox (same draws as draw_noise)
@@ -498,8 +499,8 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
         fence_after_sync();
         const uint32_t wb = wait_w();
         if (elect_one()) {
-          issue_block_ss<H1, 32>(tm + C_D1, chunk_s + b * CHUNK_BYTES, CHUNK_HALF, wb, c == 0);
-          issue_block_ss<NY, 32>(tm + C_Y0P, chunk_s + b * CHUNK_BYTES, CHUNK_HALF, wb + MAIN_BYTES, c == 0);
+          // down_1 and Wc r1 in one MMA: N = H1 + NY, columns [C_D1, C_D1 + H1) and [C_Y0P, C_Y0P + NY)
+          issue_block_ss<H1 + NY, 32>(tm + C_D1, chunk_s + b * CHUNK_BYTES, CHUNK_HALF, wb, c == 0);
           commit(&bars[CH_EMPTY + b]);
         }
         __syncwarp();

@@ -69,6 +69,8 @@ struct SlotDesc {
   int transposed;  // 0: B[n][k] = W[n0+n][k0+k] (forward);  1: B[n][k] = W[k0+k][n0+n] (dgrad: W^T)
   int klim;   // contraction indices >= klim are zero padding
   int nlim;   // rows >= nlim are zero padding
+  int slab_n; // rows of the slab this block is part of (0: N) -- the lo slab follows slab_n rows after the hi slab
+  int slab_row;  // first row of the block inside the slab
 };
 struct PackItem {
   int slot, byte_off;
@@ -81,39 +83,42 @@ __host__ __device__ inline int fwd_items(int d) { return w0_slots(d) + 40; }
 __host__ __device__ inline int bwd_items(int d) { return bwd_slots(d); }
 __host__ __device__ inline PackItem fwd_item(int d, int i) {
   const int S = w0_slots(d), kin = kin_of(d), NY = ny_of(d);
-  if (i < S) return PackItem{i, 0, SlotDesc{0, i * (H0 / S), H0 / S, 0, kin, d + 1, 0, d + 1, NOLIM}};
+  if (i < S) return PackItem{i, 0, SlotDesc{0, i * (H0 / S), H0 / S, 0, kin, d + 1, 0, d + 1, NOLIM, 0, 0}};
   i -= S;
-  if (i < 8) return PackItem{S + i, 0, SlotDesc{1, 0, H1, 32 * i, 32, H0, 0, H0, NOLIM}};
+  // down_1 block and its Wc block form ONE B operand of H1 + NY rows: D1 and Wc r1 come out of a single MMA
+  // (N = 144 / 160) into adjacent TMEM columns; a separate N = 16 MMA would re-read the whole A chunk from
+  // shared memory and cost half as much as the N = 128 one
+  if (i < 8) return PackItem{S + i, 0, SlotDesc{1, 0, H1, 32 * i, 32, H0, 0, H0, NOLIM, H1 + NY, 0}};
   i -= 8;
-  if (i < 8) return PackItem{S + i, MAIN_BYTES, SlotDesc{WC_LAYER, 0, NY, 32 * i, 32, H0, 0, H0, d}};
+  if (i < 8) return PackItem{S + i, 0, SlotDesc{WC_LAYER, 0, NY, 32 * i, 32, H0, 0, H0, d, H1 + NY, H1}};
   i -= 8;
-  if (i < 2) return PackItem{S + 8 + i, 0, SlotDesc{2, 0, H2, 64 * i, 64, H1, 0, H1, NOLIM}};
+  if (i < 2) return PackItem{S + 8 + i, 0, SlotDesc{2, 0, H2, 64 * i, 64, H1, 0, H1, NOLIM, 0, 0}};
   i -= 2;
-  if (i < 2) return PackItem{S + 10 + i, 0, SlotDesc{6, 0, H1, 32 * i, 32, H2, 0, H2, NOLIM}};
+  if (i < 2) return PackItem{S + 10 + i, 0, SlotDesc{6, 0, H1, 32 * i, 32, H2, 0, H2, NOLIM, 0, 0}};
   i -= 2;
-  if (i < 4) return PackItem{S + 12 + i, 0, SlotDesc{5, 0, H1, 32 * i, 32, H1, 0, H1, NOLIM}};
+  if (i < 4) return PackItem{S + 12 + i, 0, SlotDesc{5, 0, H1, 32 * i, 32, H1, 0, H1, NOLIM, 0, 0}};
   i -= 4;
-  if (i < 8) return PackItem{S + 16 + i, 0, SlotDesc{7, 0, H0, 16 * i, 16, H1, 0, H1, NOLIM}};
+  if (i < 8) return PackItem{S + 16 + i, 0, SlotDesc{7, 0, H0, 16 * i, 16, H1, 0, H1, NOLIM, 0, 0}};
   i -= 8;
   const int bps = MAIN_BYTES / (NY * 256);  // up_0 K-chunks per slot (8 or 4)
-  return PackItem{S + 24 + i / bps, (i % bps) * (NY * 256), SlotDesc{8, 0, NY, 32 * i, 32, H0, 0, H0, d}};
+  return PackItem{S + 24 + i / bps, (i % bps) * (NY * 256), SlotDesc{8, 0, NY, 32 * i, 32, H0, 0, H0, d, 0, 0}};
 }
 __host__ __device__ inline PackItem bwd_item(int d, int s) {
   const int S = w0_slots(d), kin = kin_of(d);
   const int slot = s;
-  if (s < S) return PackItem{slot, 0, SlotDesc{8, s * (H0 / S), H0 / S, 0, kin, H0, 1, d, NOLIM}};  // d_o1[f] = sum_j d_y0[j] W_u0[j][f]
+  if (s < S) return PackItem{slot, 0, SlotDesc{8, s * (H0 / S), H0 / S, 0, kin, H0, 1, d, NOLIM, 0, 0}};  // d_o1[f] = sum_j d_y0[j] W_u0[j][f]
   s -= S;
-  if (s < 8) return PackItem{slot, 0, SlotDesc{7, 0, H1, 32 * s, 32, H1, 1, H0, NOLIM}};   // d_o2[c] = sum_n d_y1[n] W_u1[n][c]
+  if (s < 8) return PackItem{slot, 0, SlotDesc{7, 0, H1, 32 * s, 32, H1, 1, H0, NOLIM, 0, 0}};   // d_o2[c] = sum_n d_y1[n] W_u1[n][c]
   s -= 8;
-  if (s < 4) return PackItem{slot, 0, SlotDesc{5, 0, H1, 32 * s, 32, H1, 1, H1, NOLIM}};   // d_r2[c] = sum_n d_o2[n] W_r2[n][c]
+  if (s < 4) return PackItem{slot, 0, SlotDesc{5, 0, H1, 32 * s, 32, H1, 1, H1, NOLIM, 0, 0}};   // d_r2[c] = sum_n d_o2[n] W_r2[n][c]
   s -= 4;
-  if (s < 2) return PackItem{slot, 0, SlotDesc{6, 0, H2, 64 * s, 64, H2, 1, H1, NOLIM}};   // d_r3[c] = sum_n d_y2[n] W_u2[n][c]
+  if (s < 2) return PackItem{slot, 0, SlotDesc{6, 0, H2, 64 * s, 64, H2, 1, H1, NOLIM, 0, 0}};   // d_r3[c] = sum_n d_y2[n] W_u2[n][c]
   s -= 2;
-  if (s < 2) return PackItem{slot, 0, SlotDesc{2, 0, H1, 32 * s, 32, H1, 1, H2, NOLIM}};   // d_r2[c] += sum_n d_z3[n] W_d2[n][c]
+  if (s < 2) return PackItem{slot, 0, SlotDesc{2, 0, H1, 32 * s, 32, H1, 1, H2, NOLIM, 0, 0}};   // d_r2[c] += sum_n d_z3[n] W_d2[n][c]
   s -= 2;
-  if (s < 8) return PackItem{slot, 0, SlotDesc{1, 0, H0, 16 * s, 16, H0, 1, H1, NOLIM}};   // d_r1[c] = sum_n d_z2[n] W_d1[n][c]
+  if (s < 8) return PackItem{slot, 0, SlotDesc{1, 0, H0, 16 * s, 16, H0, 1, H1, NOLIM, 0, 0}};   // d_r1[c] = sum_n d_z2[n] W_d1[n][c]
   s -= 8;
-  return PackItem{slot, 0, SlotDesc{WC_LAYER, s * (H0 / S), H0 / S, 0, kin, H0, 1, d, NOLIM}};  // d_r1[g] += sum_j d_y0[j] Wc[j][g]
+  return PackItem{slot, 0, SlotDesc{WC_LAYER, s * (H0 / S), H0 / S, 0, kin, H0, 1, d, NOLIM, 0, 0}};  // d_r1[g] += sum_j d_y0[j] Wc[j][g]
 }
 // bytes the producer copies for a slot
 __host__ __device__ inline uint32_t fwd_slot_bytes(int d, int s) {
