@@ -143,6 +143,12 @@ int socm_target_gemm_bwd_tc_f32(const float* G, const float* R, int32_t B, int32
 /* SOCM_const_M (method.py:289-369): target_i = sum_{j>=i} a_j + grad_g, i.e. M = I, dM = 0. */
 int socm_target_const_m_f32(const float* R, int32_t B, int32_t K, int32_t d, int32_t ldr,
                             float* target, int32_t ldt, void* stream);
+/* SOCM_adjoint (method.py:722-749): target[m][i] = a_i, the adjoint state of path m from the backward recursion
+ *   a_K = grad_g(x_K),  a_j = a_{j+1} + dt ((grad_f(x_j) + grad_f(x_{j+1})) / 2 + ((grad_b(x_j) + grad_b(x_{j+1})) / 2) a_{j+1})
+ * with the constant dt = T / num_steps of method.py:169.  states: [K+1][B][d].  The loss that follows is the
+ * same importance-weighted K3 as for SOCM (method.py:736-749 has the form of 692-720 with target = a). */
+int socm_target_adjoint_f32(const socm_setting* st, const float* states, int32_t B, int32_t K, float dt,
+                            float* target, int32_t ldt, void* stream);
 
 /* --- K3: UNet forward at all (K+1)B points + weighted loss + backward
  *     (replaces method.py:272-287, 692-720 and loss.backward(), main.py:323) -------------

@@ -346,7 +346,7 @@ def socm_loss(
     warm: Optional[WarmStartTable] = None,
     use_stopping_time: bool = False,
 ):
-    """Faithful restatement of SOC_Solver.loss for algorithm in {SOCM, SOCM_const_M}
+    """Faithful restatement of SOC_Solver.loss for algorithm in {SOCM, SOCM_const_M, SOCM_adjoint}
     given a finished rollout ``traj`` (the 8-tuple of :func:`rollout`).  The SOCM
     branch keeps the reference's structure on purpose -- reverse-mode ``jacrev`` for
     d/ds M and the materialised (K+1, K+1, B, d, d) integrand -- because this function
@@ -380,6 +380,23 @@ def socm_loss(
         )
         learned = -torch.einsum("ij,...j->...i", st.sigma.t(), gv)
         wanted = -torch.einsum("ij,...j->...i", st.sigma.t(), target)
+        obj = torch.sum((learned - wanted) ** 2 * weight.unsqueeze(0).unsqueeze(2)) / (K1 * B)
+        return obj, torch.mean(weight), torch.std(weight)
+
+    if algorithm == "SOCM_adjoint":                                # method.py:722-749
+        # backward recursion of the adjoint a_k along every path (trapezoid rule in f' and b'), target = a
+        gf = grad_run_cost(st, states)
+        gb = grad_drift(st, states)
+        dt = st.T / (K1 - 1)                                       # self.dt = T / num_steps (method.py:169)
+        a = grad_term_cost(st, states[-1]).clone()
+        a_vectors = torch.zeros_like(states)
+        a_vectors[-1] = a
+        for k in range(1, K1):
+            a = a + dt * ((gf[-1 - k] + gf[-k]) / 2
+                          + torch.einsum("mkl,ml->mk", (gb[-1 - k] + gb[-k]) / 2, a))
+            a_vectors[-1 - k] = a
+        learned = -torch.einsum("ij,...j->...i", st.sigma.t(), gv)
+        wanted = -torch.einsum("ij,...j->...i", st.sigma.t(), a_vectors)
         obj = torch.sum((learned - wanted) ** 2 * weight.unsqueeze(0).unsqueeze(2)) / (K1 * B)
         return obj, torch.mean(weight), torch.std(weight)
 

@@ -12,11 +12,11 @@ include/socm_b200.h (libsocm_b200.so); there is no CPU fallback.
 from .networks import FullyConnectedUNet, SigmoidMLP, TwoBoundarySigmoidMLP, WarmStartTable  # noqa: F401
 from .sde import (DoubleWell, MolecularDynamics, NeuralSDE, OU_Linear, OU_Quadratic,  # noqa: F401
                   describe_setting, make_benchmark_sde)
-from .simulate import control_objective, rollout, stochastic_trajectories  # noqa: F401
+from .simulate import control_objective, normalization_constant, rollout, stochastic_trajectories  # noqa: F401
 from .solver import SOC_Solver  # noqa: F401
 
 __all__ = [
-    "stochastic_trajectories", "control_objective", "rollout", "SOC_Solver", "NeuralSDE",
+    "stochastic_trajectories", "control_objective", "normalization_constant", "rollout", "SOC_Solver", "NeuralSDE",
     "FullyConnectedUNet", "SigmoidMLP", "TwoBoundarySigmoidMLP", "WarmStartTable",
     "OU_Quadratic", "OU_Linear", "DoubleWell", "MolecularDynamics", "describe_setting", "make_benchmark_sde",
 ]

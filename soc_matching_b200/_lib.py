@@ -57,6 +57,7 @@ PROTOTYPES = {
     "socm_target_gemm_bwd_tc_workspace_bytes": (_i64, [_i32, _i32, _i32]),
     "socm_target_gemm_bwd_tc_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp]),
     "socm_target_const_m_f32": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "socm_target_adjoint_f32": (C.c_int, [C.POINTER(Setting), _vp, _i32, _i32, _f32, _vp, _i32, _vp]),
     "socm_loss_workspace_bytes": (_i64, [C.POINTER(UNet), _i32, _i32]),
     "socm_unet_param_count": (_i64, [C.POINTER(UNet)]),
     "socm_unet_loss_fwdbwd_f32": (C.c_int, [C.POINTER(Setting), C.POINTER(UNet), C.POINTER(WarmTable), _vp, _vp,

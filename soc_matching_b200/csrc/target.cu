@@ -7,6 +7,7 @@
 //   target_gemm_kernel      target[B][ldt] = R L^T        (only K-blocks with j >= i are read)
 //   target_gemm_bwd_kernel  dL = G^T R                    (contraction over paths, split-K)
 //   target_const_m_kernel   SOCM_const_M: suffix sums (method.py:289-369)
+//   target_adjoint_kernel   SOCM_adjoint: backward recursion of the adjoint state per path (method.py:722-749)
 //   weight_stats_kernel     sum w, sum w^2, sum stop with a warp-shuffle block reduction
 // The two GEMMs here are the FP32 SIMT versions (parity path).
 #include "kernels.h"
@@ -197,6 +198,48 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// ---------------------------------------------------------------- SOCM_adjoint target (method.py:722-735)
+// One thread per path walks the grid backwards:  a_K = grad_g(x_K),
+//   a_j = a_{j+1} + dt * ((grad_f_j + grad_f_{j+1}) / 2 + ((grad_b_j + grad_b_{j+1}) / 2) a_{j+1})
+// grad_b is contracted on its last index ("mkl,ml->mk"); the OU settings return the constant A^T
+// (so the average is A^T itself), double well / molecular dynamics a diagonal.
+__global__ void __launch_bounds__(128) target_adjoint_kernel(socm_setting st, const float* __restrict__ states, int B,
+                                                             int K, float dt, float* __restrict__ target, int ldt) {
+  const int d = st.d;
+  const bool ou = st.kind == SOCM_OU_QUADRATIC || st.kind == SOCM_OU_LINEAR;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < B; m += gridDim.x * blockDim.x) {
+    float a[kMaxDim], x1[kMaxDim], x0[kMaxDim], f1[kMaxDim], f0[kMaxDim], t[kMaxDim];
+    const float* xs = states + ((size_t)K * B + m) * d;
+    for (int i = 0; i < d; ++i) x1[i] = __ldg(xs + i);
+    grad_term_cost(st, x1, 1, a);
+    grad_run_cost(st, x1, 1, f1);
+    float* row = target + (size_t)m * ldt;
+    for (int i = 0; i < d; ++i) row[K * d + i] = a[i];
+    for (int j = K - 1; j >= 0; --j) {
+      xs = states + ((size_t)j * B + m) * d;
+      for (int i = 0; i < d; ++i) x0[i] = __ldg(xs + i);
+      grad_run_cost(st, x0, 1, f0);
+      if (ou) {
+        grad_drift_dot(st, x0, 1, a, t);
+      } else {
+        for (int l = 0; l < d; ++l) {
+          const float kap = __ldg(st.kappa + l);
+          const float g = __fmul_rn(__fadd_rn(dw_drift_diag_grad(kap, x0[l]), dw_drift_diag_grad(kap, x1[l])), 0.5f);
+          t[l] = __fmul_rn(g, a[l]);
+        }
+      }
+      for (int i = 0; i < d; ++i) {
+        const float inc = __fadd_rn(__fmul_rn(__fadd_rn(f0[i], f1[i]), 0.5f), t[i]);
+        a[i] = __fadd_rn(a[i], __fmul_rn(dt, inc));
+        row[j * d + i] = a[i];
+        x1[i] = x0[i];
+        f1[i] = f0[i];
+      }
+    }
+    for (int i = (K + 1) * d; i < ldt; ++i) row[i] = 0.f;  // pitch padding
+  }
+}
+
 __global__ void __launch_bounds__(256) weight_stats_kernel(const float* __restrict__ w, const float* __restrict__ stop,
                                                            int B, int K, double* __restrict__ sums) {
   __shared__ double red[3][8];
@@ -298,6 +341,18 @@ extern "C" int socm_target_const_m_f32(const float* R, int32_t B, int32_t K, int
   if (B == 0) return SOCM_OK;
   target_const_m_kernel<<<grid_for((size_t)B * d, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(R, B, K, d, ldr,
                                                                                                        target, ldt);
+  SOCM_LAUNCH_CHECK();
+  return SOCM_OK;
+}
+
+extern "C" int socm_target_adjoint_f32(const socm_setting* st, const float* states, int32_t B, int32_t K, float dt,
+                                       float* target, int32_t ldt, void* stream_) {
+  if (int rc = validate_setting(st)) return rc;
+  SOCM_CHECK_ARG(states && target && K >= 1, "bad arguments");
+  SOCM_CHECK_ARG(ldt >= (K + 1) * st->d, "bad pitch ldt=%d", ldt);
+  if (B == 0) return SOCM_OK;
+  target_adjoint_kernel<<<grid_for((size_t)B, 128), 128, 0, static_cast<cudaStream_t>(stream_)>>>(*st, states, B, K, dt,
+                                                                                               target, ldt);
   SOCM_LAUNCH_CHECK();
   return SOCM_OK;
 }

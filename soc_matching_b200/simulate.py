@@ -116,7 +116,10 @@ def rollout(sde, x0: torch.Tensor, t: torch.Tensor, lmbd: float, *, noises: Opti
             ws.lw[0].data_ptr(), ws.lw[1].data_ptr(), ws.lw[2].data_ptr(), _lib.ptr(ws.packed), flags,
             _lib.stream_ptr())
     if timer is not None:
-        timer("rollout", 2, lib.socm_rollout_f32, *args)
+        # kernels of one call: tcgen05 path = fold + pack + rollout, FFMA tile path = pack + rollout, generic = 1
+        default_arch = (udesc.h0, udesc.h1, udesc.h2) == (256, 128, 64)
+        n_k = 1 if (force_generic or not default_arch) else (2 if (force_ffma or udesc.d > 23) else 3)
+        timer("rollout", n_k, lib.socm_rollout_f32, *args)
     else:
         _lib.check(lib.socm_rollout_f32(*args))
     del keep
@@ -147,3 +150,32 @@ def control_objective(sde, x0, ts, lmbd, batch_size, total_n_samples=65536, verb
     ws = rollout(sde, state0, ts.to(state0), lmbd, store_traj=False)
     losses = -lmbd * (ws.lw[0] + ws.lw[2])
     return torch.mean(losses), torch.std(losses) / math.sqrt(n - 1)
+
+
+def normalization_constant(sde, x0, ts, cfg, n_batches_normalization=512, ground_truth_control=None):
+    """utils.py:166-231: Monte-Carlo estimate of E[exp(log-weights)] under the current control (and, if a
+    ground-truth control is given, the importance-weighted squared control error), from
+    ``n_batches_normalization`` rollouts of the batch ``x0``.  Without a ground-truth control the rollouts
+    run in weights-only mode (no trajectory leaves the SM); they are grouped into launches of at most
+    2^17 paths.  ``cfg.method.lmbd`` is the only field of ``cfg`` that is read, as in the reference."""
+    lmbd = float(cfg.method.lmbd)
+    B, d = int(x0.shape[0]), int(x0.shape[1])
+    ts = ts.to(x0)
+    K = int(ts.shape[0]) - 1
+    per_launch = max(1, (1 << 17) // max(B, 1))
+    store = ground_truth_control is not None
+    logw, sqd = [], torch.zeros((), device=x0.device, dtype=torch.float64)
+    for k0 in range(0, n_batches_normalization, per_launch):
+        nb = min(per_launch, n_batches_normalization - k0)
+        ws = rollout(sde, x0.repeat(nb, 1), ts, lmbd, store_traj=store)
+        lw = (ws.lw[0] + ws.lw[1] + ws.lw[2]).reshape(nb, B)
+        logw.append(lw)
+        if store:
+            gt = ground_truth_control(ts, ws.states, t_is_tensor=True)[:-1].detach()
+            sqd += torch.sum(((gt - ws.controls) ** 2).double() * torch.exp(lw).double().reshape(1, -1, 1)) / (K * B)
+    log_weights = torch.cat(logw, dim=0).t()                # (B, n_batches), as torch.stack(..., dim=1)
+    weights = torch.exp(log_weights)
+    print(f"Average and std. dev. of log_weights for all batches: {torch.mean(log_weights)} {torch.std(log_weights)}")
+    n = weights.shape[0] * weights.shape[1]
+    norm_sqd_diff_mean = (sqd / n_batches_normalization).float() if store else None
+    return torch.mean(weights), torch.std(weights) / math.sqrt(n - 1), norm_sqd_diff_mean

@@ -111,12 +111,13 @@ class SOC_Solver(nn.Module):
         tc = (not self.force_ffma) and udesc.d <= 23 and (self.force_tc or (K + 1) * nb >= 65536)
         if not tc:
             return 3
+        # tcgen05: fold + pack, (K3a + K3b) per sub-launch, fold_finish
         n_tiles = (K + 1) * ((nb + 127) // 128)
         import ctypes
         sms = ctypes.c_int(0)
         _lib.check(_lib.load().socm_device_info(ctypes.byref(sms), None))
         sub = (8192 // max(int(sms.value), 1)) * max(int(sms.value), 1)   # csrc/loss_tc.cu: sub_tiles_max()
-        return 1 + 2 * ((n_tiles + sub - 1) // sub)
+        return 3 + 2 * ((n_tiles + sub - 1) // sub)
 
     def _grid(self):
         if self._pair_grid is None or self._pair_grid.t.device != self.ts.device:
@@ -127,12 +128,14 @@ class SOC_Solver(nn.Module):
     def loss(self, batch_size, compute_L2_error=False, optimal_control=None, compute_control_objective=False,
              algorithm="SOCM_const_M", add_weights=False, total_n_samples=65536, verbose=False,
              u_warm_start=None, use_warm_start=True, use_stopping_time=False):
-        if algorithm not in ("SOCM", "SOCM_const_M"):
+        if algorithm not in ("SOCM", "SOCM_const_M", "SOCM_adjoint"):
             raise NotImplementedError(
-                f"algorithm {algorithm!r}: only SOCM and SOCM_const_M are on the B200 hot path "
+                f"algorithm {algorithm!r}: SOCM, SOCM_const_M and SOCM_adjoint are on the B200 hot path "
                 "(SURVEY.md section 8; the other losses are 'next' rows)")
-        if compute_L2_error:
-            raise NotImplementedError("compute_L2_error needs the tabulated ground-truth controls (section 8f)")
+        if compute_L2_error and optimal_control is None:
+            raise ValueError("compute_L2_error=True needs optimal_control (a callable (ts, states, t_is_tensor=True))")
+        if algorithm == "SOCM_adjoint" and use_stopping_time:
+            raise NotImplementedError("SOCM_adjoint with stopping times is not defined by the reference (method.py:722-749)")
         lib = _lib.load()
         sde = self.neural_sde
         dev = self.x0.device
@@ -199,6 +202,7 @@ class SOC_Solver(nn.Module):
         x0_rep = self.x0.detach().float().reshape(1, d)
         ts_f32 = ts.float().contiguous()
         self.launch_count = 0
+        l2_sum = torch.zeros((), device=dev, dtype=torch.float64) if compute_L2_error else None
         for start in range(0, B, chunk):
             nb = min(chunk, B - start)
             if nb != wsp.B:   # ragged last chunk
@@ -220,6 +224,9 @@ class SOC_Solver(nn.Module):
             if algorithm == "SOCM_const_M":
                 self._timed("target", 1, lib.socm_target_const_m_f32, _lib.ptr(R), nb, K, d, ldr, _lib.ptr(target),
                             ldt, stream)
+            elif algorithm == "SOCM_adjoint":                  # method.py:722-735: adjoint recursion per path
+                self._timed("target", 1, lib.socm_target_adjoint_f32, desc.c_struct, _lib.ptr(wsp.states), nb, K,
+                            float(self.dt), _lib.ptr(target), ldt, stream)
             elif not stopping:
                 if self.force_ffma or self.force_generic:      # fp32 SIMT GEMM
                     self._timed("target", 1, lib.socm_target_gemm_f32, _lib.ptr(L.detach()), _lib.ptr(R), nb, K, d,
@@ -251,6 +258,8 @@ class SOC_Solver(nn.Module):
                         k2b_nb = nb
                     self._timed("target_bwd", 3, lib.socm_target_gemm_bwd_tc_f32, _lib.ptr(G), _lib.ptr(R), nb, K, d,
                                 ldr, ldt, _lib.ptr(dL), 1, k2b_ws.data_ptr(), stream)
+            if compute_L2_error:
+                l2_sum += self._l2_error_sum(sde, unet, optimal_control, warm_loss, ts_f32, wsp.states, wbuf)
             stop_all.append(wsp.stop if B <= chunk else wsp.stop.clone())
         self._injected_noise = None
         del keep
@@ -273,7 +282,23 @@ class SOC_Solver(nn.Module):
         ctrl_mean = ctrl_err = trajectory = None
         if compute_control_objective:
             ctrl_mean, ctrl_err, trajectory = self.control_objective(batch_size, total_n_samples=total_n_samples)
-        return (objective, None, ctrl_mean, ctrl_err, trajectory, mean_w, std_w, stop_indicators)
+        norm_sqd_diff = (l2_sum / ((K + 1) * B)).float() if compute_L2_error else None
+        return (objective, norm_sqd_diff, ctrl_mean, ctrl_err, trajectory, mean_w, std_w, stop_indicators)
+
+    # ------------------------------------------------------------------ evaluation metric (not on the training path)
+    def _l2_error_sum(self, sde, unet, optimal_control, warm_loss, ts, states, w):
+        """sum_{i,m} w_m |u*(t_i, x_im) - u_theta(t_i, x_im)|^2 (method.py:858-875; the caller divides by
+        (K+1) B).  u_theta = -sigma^T nabla_V [+ u_ws]: the UNet runs through socm_unet_forward_f32, the
+        ground-truth control is the caller's torch callable, the reduction is a torch op."""
+        K1, nb, d = states.shape
+        tx = torch.cat([ts.reshape(-1, 1, 1).expand(K1, nb, 1), states], dim=-1)
+        learned = -torch.einsum("ij,abj->abi", self.sigma.t().float(), unet(tx))
+        if warm_loss is not None:   # method.py:280-287: nabla_V - sigma^{-T} u_ws  =>  u_theta + u_ws
+            aff = warm_loss.c_loss.unsqueeze(1) + torch.einsum("kij,kbj->kbi", warm_loss.A_loss, states)
+            learned = learned + torch.einsum("ij,kbj->kbi", torch.inverse(self.sigma.float()), aff - sde.b(ts, states))
+        with torch.no_grad():
+            target_control = optimal_control(ts, states, t_is_tensor=True).detach()
+        return torch.sum(((target_control - learned) ** 2).double() * w.double().reshape(1, -1, 1))
 
     # ------------------------------------------------------------------ stopping-time target (torch side)
     def _stopping_target(self, sde, wsp, R, ts, K, d, nb):

@@ -78,7 +78,7 @@ CASES = [  # kind, d, K, B, dense sigma
 
 
 @pytest.mark.parametrize("kind,d,K,B,dense", CASES)
-@pytest.mark.parametrize("algo", ["SOCM", "SOCM_const_M"])
+@pytest.mark.parametrize("algo", ["SOCM", "SOCM_const_M", "SOCM_adjoint"])
 def test_default_width_matches_oracle(kind, d, K, B, dense, algo):
     st = random_setting(kind, d, seed=d + K, dense_sigma=dense)
     hd, hm = [256, 128, 64], [128, 128]
@@ -148,3 +148,58 @@ def test_unsupported_requests_raise():
         solver.loss(8, algorithm="rel_entropy")
     with pytest.raises(sb._lib.SocmError):
         solver.loss(8, algorithm="SOCM", use_stopping_time=True)
+
+
+def test_l2_error_and_normalization_constant():
+    """Evaluation-side rows of SURVEY.md section 8f: the importance-weighted L2 error of ``loss`` (method.py:858-875)
+    and ``normalization_constant`` (utils.py:166-231) against the same formulas evaluated with torch on the
+    trajectories the kernels produced (the rollout itself is pinned by tests/test_gpu_rollout.py)."""
+    import math
+    from types import SimpleNamespace
+    import soc_matching_b200 as sb
+    from soc_matching_b200 import simulate
+    d, K, B = 4, 20, 48
+    st = random_setting("ou_quadratic", d, seed=11)
+    hd, hm = [24, 16, 8], [12, 12]
+    unet, mnet = seeded_unet(d, hd, 3), seeded_mnet(d, hm, 4, 0.1)
+    gam = {"gamma": torch.tensor([2.0]), "gamma2": torch.tensor([1.0]), "gamma3": torch.tensor([1.0])}
+    sde = make_product_sde(st, unet, mnet, gam, hd, hm, DEV)
+    x0 = 0.3 * torch.ones(d, device=DEV)
+    Kmat = torch.randn(d, d, generator=torch.Generator().manual_seed(1)).to(DEV) * 0.3
+
+    def optimal_control(ts, states, t_is_tensor=True):       # any torch callable with the reference's signature
+        return -torch.einsum("ij,abj->abi", Kmat, states) * (1.0 - ts.reshape(-1, 1, 1))
+
+    solver = sb.SOC_Solver(sde, x0, None, T=1.0, num_steps=K, lmbd=st.lmbd, d=d, sigma=sde.sigma)
+    noises = torch.randn(K, B, d, generator=torch.Generator().manual_seed(5)).to(DEV)
+    solver.inject_noise(noises)
+    out = solver.loss(B, compute_L2_error=True, optimal_control=optimal_control, algorithm="SOCM_adjoint")
+    ts = torch.linspace(0, 1.0, K + 1)
+    traj = orc.rollout(st, unet, x0.cpu().repeat(B, 1), ts, noises=noises.cpu())
+    gv = orc.nabla_v_all(st, unet, ts, traj[0], None)
+    learned = -torch.einsum("ij,abj->abi", st.sigma.t(), gv)
+    w = torch.exp(traj[4] + traj[5] + traj[6])
+    want = torch.sum((optimal_control(ts, traj[0]).cpu() if False else
+                      (-torch.einsum("ij,abj->abi", Kmat.cpu(), traj[0]) * (1.0 - ts.reshape(-1, 1, 1))) - learned) ** 2
+                     * w.reshape(1, -1, 1)) / ((K + 1) * B)
+    assert abs(float(out[1]) - float(want)) <= 1e-4 * abs(float(want)), (float(out[1]), float(want))
+
+    # normalization_constant: replay its rollouts with the same Philox keys
+    cfg = SimpleNamespace(method=SimpleNamespace(lmbd=st.lmbd))
+    xb = x0.repeat(B, 1)
+    c0 = simulate._SEED_COUNTER[0]
+    nc, nc_err, sqd = sb.normalization_constant(sde, xb, solver.ts, cfg, n_batches_normalization=6,
+                                                ground_truth_control=optimal_control)
+    simulate._SEED_COUNTER[0] = c0
+    ws = simulate.rollout(sde, xb.repeat(6, 1), solver.ts, st.lmbd)
+    lw = (ws.lw[0] + ws.lw[1] + ws.lw[2])
+    wts = torch.exp(lw)
+    assert abs(float(nc) - float(wts.mean())) <= 1e-6 * float(wts.mean())
+    assert abs(float(nc_err) - float(wts.std() / math.sqrt(wts.numel() - 1))) <= 1e-5 * float(nc_err)
+    gt = optimal_control(solver.ts, ws.states)[:-1]
+    want_sqd = torch.sum((gt - ws.controls) ** 2 * wts.reshape(1, -1, 1)) / (K * B) / 6
+    assert abs(float(sqd) - float(want_sqd)) <= 1e-5 * abs(float(want_sqd))
+    # weights-only mode draws the same paths: same constant without a ground-truth control
+    simulate._SEED_COUNTER[0] = c0
+    nc2, _, none = sb.normalization_constant(sde, xb, solver.ts, cfg, n_batches_normalization=6)
+    assert none is None and abs(float(nc2) - float(nc)) <= 1e-6 * float(nc)
