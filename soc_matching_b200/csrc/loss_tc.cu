@@ -54,7 +54,12 @@ enum Bar {
   D4A_FULL, Y0_FULL,
   // backward
   DY0_FULL, BD0_FULL, BDO2_FULL, BO2_FULL, BR2A_FULL, BY2_FULL, BD3_FULL, BZ3_FULL, BR2B_FULL, BZ2_FULL,
-  BD1B_FULL, N_BARS
+  BD1B_FULL,
+  // first column half of a 128-wide A operand is ready (the MMAs over its K blocks start while the epilogue
+  // threads still work on the second half)
+  // (only where the next layer's accumulator does not overlap the columns the second half is still read from:
+  //  up_1 and down_1^T write [256,512) and must wait for the whole epilogue)
+  R2H_FULL, BO2H_FULL, BY2H_FULL, N_BARS
 };
 constexpr int NT = 320, NE = 256;
 constexpr uint32_t C_SA = 0, C_D1 = 256, C_D2 = 256, C_D3 = 256, C_R3 = 384, C_D4 = 256;
@@ -148,8 +153,9 @@ __global__ void __launch_bounds__(k3::NT, 1)
     }
     mbar_init(&bars[XIN_FULL], TP / 32);
     mbar_init(&bars[DY0_FULL], TP / 32);
-    const int e2m[] = {R2_FULL, R3_FULL, Y2_FULL, O2_FULL, BO2_FULL, BY2_FULL, BZ3_FULL, BZ2_FULL};
-    for (int i = 0; i < 8; ++i) mbar_init(&bars[e2m[i]], NE / 32);
+    const int e2m[] = {R2_FULL, R3_FULL, Y2_FULL, O2_FULL, BO2_FULL, BY2_FULL, BZ3_FULL, BZ2_FULL,
+                       R2H_FULL, BO2H_FULL, BY2H_FULL};
+    for (int i = 0; i < 11; ++i) mbar_init(&bars[e2m[i]], NE / 32);
     const int m2e[] = {D0_FULL, D1_FULL, D2_FULL, D3A_FULL, D3B_FULL, D4A_FULL, Y0_FULL, BD0_FULL,
                        BDO2_FULL, BR2A_FULL, BD3_FULL, BR2B_FULL, BD1B_FULL};
     for (int i = 0; i < 13; ++i) mbar_init(&bars[m2e[i]], 1);
@@ -275,7 +281,7 @@ __global__ void __launch_bounds__(k3::NT, 1)
         }
 #pragma unroll 1
         for (int i = 0; i < 2; ++i) {
-          const int cb = 2 * h + i;
+          const int cb = 2 * i + h;  // iteration 0 covers columns [0,64), iteration 1 [64,128)
           float v[32];
           tmem_ld32(lane_t + C_D1 + 32 * cb, reinterpret_cast<uint32_t*>(v));
           tmem_wait_ld();
@@ -283,6 +289,11 @@ __global__ void __launch_bounds__(k3::NT, 1)
           m_r2 |= (uint64_t)positive_bits<32>(v) << (32 * i);
           store_split32(lane_t + C_SA + 32 * cb, lane_t + C_SA + 128 + 32 * cb, v);
           store_fb32(sq + (FB_R2 + cb) * FB_BYTES, ro, v);
+          if (i == 0) {
+            tmem_wait_st();
+            fence_before_sync();
+            warp_arrive(&bars[R2H_FULL]);
+          }
         }
         tmem_wait_st();
         fence_before_sync();
@@ -311,7 +322,7 @@ __global__ void __launch_bounds__(k3::NT, 1)
         fence_after_sync();
 #pragma unroll 1
         for (int i = 0; i < 2; ++i) {
-          const int cb = 2 * h + i;
+          const int cb = 2 * i + h;  // iteration 0 covers columns [0,64), iteration 1 [64,128)
           float v[32];
           tmem_ld32(lane_t + C_D3 + 32 * cb, reinterpret_cast<uint32_t*>(v));
           tmem_wait_ld();
@@ -329,7 +340,7 @@ __global__ void __launch_bounds__(k3::NT, 1)
         fence_after_sync();
 #pragma unroll 1
         for (int i = 0; i < 2; ++i) {
-          const int cb = 2 * h + i;
+          const int cb = 2 * i + h;  // iteration 0 covers columns [0,64), iteration 1 [64,128)
           float v[32];
           tmem_ld32(lane_t + C_D3 + 32 * cb, reinterpret_cast<uint32_t*>(v));
           tmem_wait_ld();
@@ -452,7 +463,7 @@ __global__ void __launch_bounds__(k3::NT, 1)
         fence_after_sync();
 #pragma unroll 1
         for (int i = 0; i < 2; ++i) {
-          const int cb = 2 * h + i;
+          const int cb = 2 * i + h;  // iteration 0 covers columns [0,64), iteration 1 [64,128)
           float v[32];
           tmem_ld32(lane_t + C_DO2 + 32 * cb, reinterpret_cast<uint32_t*>(v));
           tmem_wait_ld();
@@ -460,6 +471,11 @@ __global__ void __launch_bounds__(k3::NT, 1)
           store_fb32(sq + (FB_DO2 + cb) * FB_BYTES, ro, v);
           apply_bits<32>(v, (uint32_t)(m_y2 >> (32 * i)));
           store_fb32(sq + (FB_DY2 + cb) * FB_BYTES, ro, v);
+          if (i == 0) {
+            tmem_wait_st();
+            fence_before_sync();
+            warp_arrive(&bars[BO2H_FULL]);
+          }
         }
         tmem_wait_st();
         fence_before_sync();
@@ -471,12 +487,17 @@ __global__ void __launch_bounds__(k3::NT, 1)
         fence_after_sync();
 #pragma unroll 1
         for (int i = 0; i < 2; ++i) {
-          const int cb = 2 * h + i;
+          const int cb = 2 * i + h;  // iteration 0 covers columns [0,64), iteration 1 [64,128)
           float v[32];
           tmem_ld32(lane_t + C_DO2 + 32 * cb, reinterpret_cast<uint32_t*>(v));
           tmem_wait_ld();
           apply_bits<32>(v, (uint32_t)(m_y2 >> (32 * i)));
           store_split32(lane_t + C_SA + 32 * cb, lane_t + C_SA + 128 + 32 * cb, v);
+          if (i == 0) {
+            tmem_wait_st();
+            fence_before_sync();
+            warp_arrive(&bars[BY2H_FULL]);
+          }
         }
         tmem_wait_st();
         fence_before_sync();
@@ -504,7 +525,7 @@ __global__ void __launch_bounds__(k3::NT, 1)
         fence_after_sync();
 #pragma unroll 1
         for (int i = 0; i < 2; ++i) {
-          const int cb = 2 * h + i;
+          const int cb = 2 * i + h;  // iteration 0 covers columns [0,64), iteration 1 [64,128)
           float v[32];
           tmem_ld32(lane_t + C_DR2 + 32 * cb, reinterpret_cast<uint32_t*>(v));
           tmem_wait_ld();
@@ -627,8 +648,9 @@ __global__ void __launch_bounds__(k3::NT, 1)
       signal(D0_FULL);
       chunk_layer_128(C_D1, true);  // down_1 (+ Wc r1)
       signal(D1_FULL);
-      wait_e(R2_FULL, ph);          // down_2: A = r2 (TMEM)
+      wait_e(R2H_FULL, ph);         // down_2: A = r2 (TMEM); K block 0 = columns [0,64) is ready first
       for (int j = 0; j < 2; ++j) {
+        if (j == 1) wait_e(R2_FULL, ph);
         const uint32_t wb = wait_w();
         if (elect_one()) issue_block_ts<H2, 64>(tm + C_D2, tm + C_SA + 64 * j, tm + C_SA + 128 + 64 * j, wb, j == 0);
         __syncwarp();
@@ -667,16 +689,18 @@ __global__ void __launch_bounds__(k3::NT, 1)
       signal(BD0_FULL);
       chunk_layer_128(C_DO2, false);  // d_o2 = d_y1 W_u1
       signal(BDO2_FULL);
-      wait_e(BO2_FULL, ph);          // d_r2 = d_o2 W_r2
+      wait_e(BO2H_FULL, ph);         // d_r2 = d_o2 W_r2
       for (int j = 0; j < 4; ++j) {
+        if (j == 2) wait_e(BO2_FULL, ph);
         const uint32_t wb = wait_w();
         if (elect_one()) issue_block_ts<H1, 32>(tm + C_DR2, tm + C_SA + 32 * j, tm + C_SA + 128 + 32 * j, wb, j == 0);
         __syncwarp();
         release_w();
       }
       signal(BR2A_FULL);
-      wait_e(BY2_FULL, ph);          // d_r3 = d_y2 W_u2  (N = 64)
+      wait_e(BY2H_FULL, ph);         // d_r3 = d_y2 W_u2  (N = 64)
       for (int j = 0; j < 2; ++j) {
+        if (j == 1) wait_e(BY2_FULL, ph);
         const uint32_t wb = wait_w();
         if (elect_one()) issue_block_ts<H2, 64>(tm + C_DR3, tm + C_SA + 64 * j, tm + C_SA + 128 + 64 * j, wb, j == 0);
         __syncwarp();

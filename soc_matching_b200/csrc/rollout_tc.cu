@@ -89,7 +89,9 @@ constexpr int SM_SMALL = SM_XIN + MAX_KIN * 1024;  // xin: hi + lo, 128 x kin fl
 enum Bar {
   W_FULL = 0, W_EMPTY = W_FULL + NSTAGE, CH_FULL = W_EMPTY + NSTAGE, CH_EMPTY = CH_FULL + 2,
   XIN_FULL = CH_EMPTY + 2, D0_FULL, D1_FULL, R2_FULL, D2_FULL, R3_FULL, D3A_FULL, Y2_FULL, D3B_FULL, O2_FULL,
-  D4A_FULL, Y0_FULL, N_BARS
+  D4A_FULL, Y0_FULL,
+  R2H_FULL,  // first column half of r2 is ready: down_2 starts on its K block 0 while the second half is written
+  N_BARS
 };
 __host__ __device__ inline int rollout_tc_smem_bytes(int d) { return SM_SMALL + small_tc(d).total * 4 + N_BARS * 8 + 16; }
 
@@ -168,8 +170,8 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
       mbar_init(&bars[CH_EMPTY + b], 1);
     }
     mbar_init(&bars[XIN_FULL], TP / 32);
-    const int e2m[] = {R2_FULL, R3_FULL, Y2_FULL, O2_FULL};
-    for (int i = 0; i < 4; ++i) mbar_init(&bars[e2m[i]], NE / 32);
+    const int e2m[] = {R2_FULL, R3_FULL, Y2_FULL, O2_FULL, R2H_FULL};
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[e2m[i]], NE / 32);
     const int m2e[] = {D0_FULL, D1_FULL, D2_FULL, D3A_FULL, D3B_FULL, D4A_FULL, Y0_FULL};
     for (int i = 0; i < 7; ++i) mbar_init(&bars[m2e[i]], 1);
     mbar_init_fence();
@@ -288,12 +290,18 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
           for (int j = 0; j < KIN; ++j) au[j] = yp[j];
         }
 #pragma unroll 1
-        for (int cb = 2 * h; cb < 2 * h + 2; ++cb) {
+        for (int i = 0; i < 2; ++i) {
+          const int cb = 2 * i + h;  // iteration 0 covers columns [0,64) = K block 0 of down_2
           float v[32];
           tmem_ld32(lane_t + C_D1 + 32 * cb, reinterpret_cast<uint32_t*>(v));
           tmem_wait_ld();
           bias_relu32(v, sm_small + so.b_d1 + 32 * cb);
           store_split32(lane_t + C_SA + 32 * cb, lane_t + C_SA + 128 + 32 * cb, v);
+          if (i == 0) {
+            tmem_wait_st();
+            fence_before_sync();
+            warp_arrive(&bars[R2H_FULL]);
+          }
         }
         tmem_wait_st();
         fence_before_sync();
@@ -335,7 +343,8 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
         PROF_MARK(7);
         fence_after_sync();
 #pragma unroll 1
-        for (int cb = 2 * h; cb < 2 * h + 2; ++cb) {
+        for (int i = 0; i < 2; ++i) {
+          const int cb = 2 * i + h;  // iteration 0 covers columns [0,64) = K blocks 0..3 of up_1
           float v[32];
           tmem_ld32(lane_t + C_D3 + 32 * cb, reinterpret_cast<uint32_t*>(v));
           tmem_wait_ld();
@@ -511,10 +520,14 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
       __syncwarp();
       PROF_MARK(2);
       // ---- M2: down_2, A = r2 (TMEM), 2 blocks of K = 64
-      mbar_wait(&bars[R2_FULL], ph);
+      mbar_wait(&bars[R2H_FULL], ph);
       PROF_MARK(3);
       fence_after_sync();
       for (int j = 0; j < 2; ++j) {
+        if (j == 1) {
+          mbar_wait(&bars[R2_FULL], ph);
+          fence_after_sync();
+        }
         const uint32_t wb = wait_w();
         if (elect_one()) issue_block_ts<H2, 64>(tm + C_D2, tm + C_SA + 64 * j, tm + C_SA + 128 + 64 * j, wb, j == 0);
         __syncwarp();
