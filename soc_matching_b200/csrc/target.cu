@@ -15,48 +15,86 @@
 namespace socm {
 
 // ---------------------------------------------------------------- R and w
+// Per (step j, path m):  c = sigma^{-T}(sqrt(lmbd eff) eps + eff u),  a = eff grad_f - grad_b . c   
+__device__ __forceinline__ void prep_point(const socm_setting& st, float sq_lmbd, const float* __restrict__ states,
+                                           const float* __restrict__ noises, const float* __restrict__ controls,
+                                           const float* __restrict__ eff_dt, int B, int j, int m, float* a_out,
+                                           float* c_out) {
+  const int d = st.d;
+  float x[kMaxDim], t0[kMaxDim], t1[kMaxDim];
+  const float* xs = states + ((size_t)j * B + m) * d;
+  for (int i = 0; i < d; ++i) x[i] = __ldg(xs + i);
+  const float eff = __ldg(eff_dt + (size_t)j * B + m);
+  const float ce = sq_lmbd * sqrtf(eff);
+  const float* ep = noises + ((size_t)j * B + m) * d;
+  const float* up = controls + ((size_t)j * B + m) * d;
+  if (st.sigma_is_identity) {
+    for (int i = 0; i < d; ++i) c_out[i] = fmaf(ce, __ldg(ep + i), eff * __ldg(up + i));
+  } else {
+    for (int i = 0; i < d; ++i) t0[i] = fmaf(ce, __ldg(ep + i), eff * __ldg(up + i));
+    matvec_t(st.sigma_inv, d, t0, c_out);  // sigma^{-T} (.)
+  }
+  grad_run_cost(st, x, 1, t0);
+  grad_drift_dot(st, x, 1, c_out, t1);
+  for (int i = 0; i < d; ++i) a_out[i] = fmaf(eff, t0[i], -t1[i]);
+}
+
+// R[m][2jd .. 2jd+2d) = [a_j c_j] for j < K.  A block owns 32 paths x TJ steps: the inputs are read with the
+// paths along the lanes (states / noises / controls are [step][path][d]: coalesced), staged in shared memory
+// and written with the row of a path along the lanes (R is [path][ldr]: TJ * 2d contiguous floats per path),
+// so both sides move whole 128-byte lines.  HBM-bound: 12d + 4 bytes read, 8d bytes written per (j, m).
+constexpr int PREP_TM = 32, PREP_ROW = 320;  // paths per block, floats of a staged row (TJ = PREP_ROW / 2d steps)
 __global__ void __launch_bounds__(256) target_prep_kernel(socm_setting st, const float* __restrict__ states,
                                                           const float* __restrict__ noises,
                                                           const float* __restrict__ controls,
-                                                          const float* __restrict__ eff_dt,
-                                                          const float* __restrict__ lw_det,
-                                                          const float* __restrict__ lw_sto,
-                                                          const float* __restrict__ lw_term, int B, int K,
-                                                          float* __restrict__ R, int ldr, float* __restrict__ w) {
-  const int d = st.d;
+                                                          const float* __restrict__ eff_dt, int B, int K,
+                                                          float* __restrict__ R, int ldr) {
+  __shared__ float buf[PREP_TM][PREP_ROW + 1];  // +1: the lanes of phase 1 hit different banks
+  const int d = st.d, TJ = PREP_ROW / (2 * d);
   const float sq_lmbd = sqrtf(st.lmbd);
-  const size_t total = (size_t)(K + 1) * B;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
-    const int j = (int)(idx / B), m = (int)(idx - (size_t)j * B);
-    float x[kMaxDim], t0[kMaxDim], t1[kMaxDim];
-    const float* xs = states + ((size_t)j * B + m) * d;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_mt = (B + PREP_TM - 1) / PREP_TM, n_jt = (K + TJ - 1) / TJ;
+  for (int tile = blockIdx.x; tile < n_mt * n_jt; tile += gridDim.x) {
+    const int jt = tile / n_mt, mt = tile - jt * n_mt;  // consecutive blocks: consecutive path tiles of one step range
+    const int j0 = jt * TJ, m0 = mt * PREP_TM;
+    const int nj = min(TJ, K - j0);
+    const int m = m0 + lane;
+    for (int tj = warp; tj < nj; tj += 8) {
+      if (m < B) {
+        float a[kMaxDim], c[kMaxDim];
+        prep_point(st, sq_lmbd, states, noises, controls, eff_dt, B, j0 + tj, m, a, c);
+        for (int i = 0; i < d; ++i) {
+          buf[lane][tj * 2 * d + i] = a[i];
+          buf[lane][tj * 2 * d + d + i] = c[i];
+        }
+      }
+    }
+    __syncthreads();
+    const int row_len = nj * 2 * d;
+    for (int r = warp; r < PREP_TM && m0 + r < B; r += 8) {
+      float* dst = R + (size_t)(m0 + r) * ldr + (size_t)2 * j0 * d;
+      for (int i = lane; i < row_len; i += 32) dst[i] = buf[r][i];
+    }
+    __syncthreads();
+  }
+}
+
+// last column block of R (grad_g at the terminal state), the pitch padding, and the importance weights
+__global__ void __launch_bounds__(256) target_prep_tail_kernel(socm_setting st, const float* __restrict__ states,
+                                                               const float* __restrict__ lw_det,
+                                                               const float* __restrict__ lw_sto,
+                                                               const float* __restrict__ lw_term, int B, int K,
+                                                               float* __restrict__ R, int ldr, float* __restrict__ w) {
+  const int d = st.d;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < B; m += gridDim.x * blockDim.x) {
+    float x[kMaxDim], t0[kMaxDim];
+    const float* xs = states + ((size_t)K * B + m) * d;
     for (int i = 0; i < d; ++i) x[i] = __ldg(xs + i);
     float* row = R + (size_t)m * ldr;
-    if (j == K) {
-      grad_term_cost(st, x, 1, t0);
-      for (int i = 0; i < d; ++i) row[2 * K * d + i] = t0[i];
-      for (int i = (2 * K + 1) * d; i < ldr; ++i) row[i] = 0.f;  // pitch padding
-      if (w) w[m] = expf(__fadd_rn(__fadd_rn(__ldg(lw_det + m), __ldg(lw_sto + m)), __ldg(lw_term + m)));
-      continue;
-    }
-    const float eff = __ldg(eff_dt + (size_t)j * B + m);
-    const float ce = sq_lmbd * sqrtf(eff);
-    const float* ep = noises + ((size_t)j * B + m) * d;
-    const float* up = controls + ((size_t)j * B + m) * d;
-    float c[kMaxDim];
-    if (st.sigma_is_identity) {
-      for (int i = 0; i < d; ++i) c[i] = fmaf(ce, __ldg(ep + i), eff * __ldg(up + i));
-    } else {
-      for (int i = 0; i < d; ++i) t0[i] = fmaf(ce, __ldg(ep + i), eff * __ldg(up + i));
-      matvec_t(st.sigma_inv, d, t0, c);  // sigma^{-T} (.)
-    }
-    grad_run_cost(st, x, 1, t0);
-    grad_drift_dot(st, x, 1, c, t1);
-    for (int i = 0; i < d; ++i) {
-      row[2 * j * d + i] = fmaf(eff, t0[i], -t1[i]);
-      row[(2 * j + 1) * d + i] = c[i];
-    }
+    grad_term_cost(st, x, 1, t0);
+    for (int i = 0; i < d; ++i) row[2 * K * d + i] = t0[i];
+    for (int i = (2 * K + 1) * d; i < ldr; ++i) row[i] = 0.f;  // pitch padding
+    if (w) w[m] = expf(__fadd_rn(__fadd_rn(__ldg(lw_det + m), __ldg(lw_sto + m)), __ldg(lw_term + m)));
   }
 }
 
@@ -291,8 +329,14 @@ extern "C" int socm_target_prep_f32(const socm_setting* st, const float* states,
   SOCM_CHECK_ARG(!w || (logw_det && logw_sto && logw_term), "w requested but log-weights missing");
   SOCM_CHECK_ARG(ldr >= (2 * K + 1) * st->d && ldr % 4 == 0, "ldr=%d must be >= (2K+1)d and a multiple of 4", ldr);
   if (B == 0) return SOCM_OK;
-  target_prep_kernel<<<grid_for((size_t)(K + 1) * B, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      *st, states, noises, controls, eff_dt, logw_det, logw_sto, logw_term, B, K, R, ldr, w);
+  SOCM_CHECK_ARG(2 * st->d <= PREP_ROW, "d=%d too large for the staged rows", st->d);
+  const int tj = PREP_ROW / (2 * st->d);
+  const size_t tiles = (size_t)((B + PREP_TM - 1) / PREP_TM) * ((K + tj - 1) / tj);
+  target_prep_kernel<<<grid_for(tiles * 256, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      *st, states, noises, controls, eff_dt, B, K, R, ldr);
+  SOCM_LAUNCH_CHECK();
+  target_prep_tail_kernel<<<grid_for((size_t)B, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      *st, states, logw_det, logw_sto, logw_term, B, K, R, ldr, w);
   SOCM_LAUNCH_CHECK();
   return SOCM_OK;
 }

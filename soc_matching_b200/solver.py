@@ -215,7 +215,7 @@ class SOC_Solver(nn.Module):
             simulate.rollout(sde, x0_rep.expand(nb, d).contiguous(), ts, self.lmbd, noises=noises, seed=seed,
                              path_offset=start + self.path_offset, desc=desc, workspace=wsp,
                              force_generic=self.force_generic, force_ffma=self.force_ffma, timer=self._timed)
-            self._timed("prep", 1, lib.socm_target_prep_f32,
+            self._timed("prep", 2, lib.socm_target_prep_f32,
                         desc.c_struct, _lib.ptr(wsp.states), _lib.ptr(wsp.noises), _lib.ptr(wsp.controls),
                         _lib.ptr(wsp.eff_dt), wsp.lw[0].data_ptr(), wsp.lw[1].data_ptr(), wsp.lw[2].data_ptr(), nb, K,
                         _lib.ptr(R), ldr, _lib.ptr(wbuf), stream)
