@@ -42,6 +42,16 @@ def timeit(fn, n=4):
 t3 = timeit(k3)
 n_tiles = (K + 1) * (B // 128)
 print(f"{os.environ.get('SOCM_B200_LIB', 'default')}: B={B} K3 {t3:.2f} ms ({n_tiles} tiles, {t3 * 1e3 / (n_tiles / 148):.1f} us/tile/SM)", end="")
+if os.environ.get("AB_K2", "1") == "1":
+    B2 = 37888
+    ldr = ((2 * K + 1) * d + 3) // 4 * 4
+    G2 = torch.randn(B2, ldt, device=DEV, generator=g)
+    R2 = torch.randn(B2, ldr, device=DEV, generator=g)
+    dL = torch.zeros((K + 1) * d, ldr, device=DEV)
+    wsb = torch.empty(int(lib.socm_target_gemm_bwd_tc_workspace_bytes(B2, K, d)), device=DEV, dtype=torch.uint8)
+    t2 = timeit(lambda: _lib.check(lib.socm_target_gemm_bwd_tc_f32(G2.data_ptr(), R2.data_ptr(), B2, K, d, ldr, ldt,
+                                                                    dL.data_ptr(), 1, wsb.data_ptr(), _lib.stream_ptr())), 3)
+    print(f"  K2b {t2:.2f} ms for {B2} paths", end="")
 if os.environ.get("AB_K1", "1") == "1":
     from helpers import make_product_sde, random_setting, seeded_mnet
     stg = random_setting("double_well", d, seed=3)

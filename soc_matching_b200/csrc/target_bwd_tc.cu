@@ -53,7 +53,7 @@ constexpr int KB_STAGES = 2;
 constexpr int KB_RAW = 16384 + 32768;        // A (128 features) | B (256 features), 32 paths each
 constexpr int KB_STAGE_BYTES = 2 * KB_RAW;   // raw (-> hi in place) + lo
 constexpr int KB_SMEM = KB_STAGES * KB_STAGE_BYTES + 1024 + 256;
-constexpr int KB_NT = 192;
+constexpr int KB_NT = 320;                   // warps 0-3 split + flush, 4 MMA, 5 producer, 6-9 split
 constexpr int KB_SEG = 32;                   // stages (of 4 K steps x 3 MMAs) per TMEM accumulation segment
 constexpr uint64_t KB_SW128 = 2ull << 61;
 
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(KB_NT, 1)
     for (int s = 0; s < KB_STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
-      mbar_init(&split[s], 4);
+      mbar_init(&split[s], 8);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
@@ -147,11 +147,13 @@ __global__ void __launch_bounds__(KB_NT, 1)
     }
   } else {
     // ===================================================== warps 0-3: hi/lo split of every stage, then the flush
-    const uint32_t lane_t = tm + ((uint32_t)(warp * 32) << 16);
+    const bool flusher = warp < 4;
+    const int sid = flusher ? tid : tid - 64;       // 0..255 among the split threads
+    const uint32_t lane_t = tm + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t it = 0, ia = 0;
     for (int bi = blockIdx.x; bi < n_blocks; bi += gridDim.x) {
       const int rb = blocks[bi] & 0xFFFF, cb = blocks[bi] >> 16;
-      const int n = 128 * rb + tid;                 // row of dL owned by this thread
+      const int n = 128 * rb + (tid & 127);         // row of dL owned by this (flusher) thread
       const int k_lo = 2 * (n / g.d) * g.d;         // columns left of it are structurally zero
       for (int sg = 0; sg < n_seg; ++sg, ++ia) {
         const int q1 = (sg + 1) * KB_SEG < n_stage_blk ? (sg + 1) * KB_SEG : n_stage_blk;
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(KB_NT, 1)
           mbar_wait(&full[s], (it / KB_STAGES) & 1);
           float4* raw = reinterpret_cast<float4*>(smem + s * KB_STAGE_BYTES);
           float4* lo = reinterpret_cast<float4*>(smem + s * KB_STAGE_BYTES + KB_RAW);
-          for (int j = tid; j < KB_RAW / 16; j += 128) {
+          for (int j = sid; j < KB_RAW / 16; j += 256) {
             const float4 x = raw[j];
             float4 hi, y;
             hi.x = tf32_rn(x.x); hi.y = tf32_rn(x.y); hi.z = tf32_rn(x.z); hi.w = tf32_rn(x.w);
@@ -172,6 +174,7 @@ __global__ void __launch_bounds__(KB_NT, 1)
           __syncwarp();
           if ((tid & 31) == 0) mbar_arrive(&split[s]);
         }
+        if (!flusher) continue;
         // ---- flush this segment's partial sums: dL[n][256 cb + c] += acc
         const uint32_t a = ia & 1;
         mbar_wait(&acc_full[a], (ia >> 1) & 1);
@@ -182,11 +185,22 @@ __global__ void __launch_bounds__(KB_NT, 1)
           tmem_ld32(lane_t + a * 256 + c0, reinterpret_cast<uint32_t*>(v));
           tmem_wait_ld();
           if (n < g.nrows) {
+            // fire-and-forget adds (this thread is the only writer of its row segment): a read-modify-write
+            // here kept the split warps waiting on global loads once per segment
             float* dst = dL + (size_t)n * ldr + 256 * cb + c0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 32; j += 4) {
               const int k = 256 * cb + c0 + j;
-              if (k < g.kdim && k >= k_lo) dst[j] += v[j];
+              if (k >= k_lo && k + 3 < g.kdim) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]),
+                             "f"(v[j + 2]), "f"(v[j + 3])
+                             : "memory");
+              } else {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                  if (k + jj < g.kdim && k + jj >= k_lo)
+                    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + j + jj), "f"(v[j + jj]) : "memory");
+              }
             }
           }
         }

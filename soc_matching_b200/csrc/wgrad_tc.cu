@@ -261,9 +261,12 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
             for (int j = sid; j < n_f4; j += 256) {
               const float4 x = raw[f4_begin + j];
               float4 hi, y;
-              hi.x = tf32_rn(x.x); hi.y = tf32_rn(x.y); hi.z = tf32_rn(x.z); hi.w = tf32_rn(x.w);
+              // The MMA reads the raw fp32 value truncated to tf32 (hi = trunc(x)), so only lo = x - trunc(x) has to
+              // be written: x = hi + lo exactly, lo < 2^-10 |x| and the hardware keeps 11 bits of it, i.e. the pair
+              // represents x to 2^-20 (one-sided).  A round-to-nearest hi would halve that but costs a second
+              // shared-memory write of every operand, and this kernel is bound by shared-memory bandwidth.
+              hi.x = tf32_hi(x.x); hi.y = tf32_hi(x.y); hi.z = tf32_hi(x.z); hi.w = tf32_hi(x.w);
               y.x = x.x - hi.x; y.y = x.y - hi.y; y.z = x.z - hi.z; y.w = x.w - hi.w;
-              raw[f4_begin + j] = hi;  // round-to-nearest split (unbiased; the MMA would truncate)
               lo[f4_begin + j] = y;
             }
           }
