@@ -170,8 +170,8 @@ __global__ void __launch_bounds__(k3::NT, 1)
 
   if (warp < 8) {
     // =================================================================== E: epilogue / point threads
-    auto e_program = [&](auto h_const) {
-      constexpr int h = decltype(h_const)::value;  // column half; h == 0 threads own the point
+    auto e_program = [&](const int h) {  // column half; h == 0 threads own the point.  ONE copy of the code for both
+      // halves: the two warps of a scheduler (an owner and a helper) then fetch the same instructions
       const int p = tid & (TP - 1), r = tid & 31, q = (tid >> 5) & 3;
       const RowOff ro(r);
       const uint32_t lane_t = tm + ((uint32_t)(q * 32) << 16);
@@ -571,8 +571,7 @@ __global__ void __launch_bounds__(k3::NT, 1)
         if ((tid & 31) == 0 && loss_acc != 0.0) atomicAdd(a.loss_sums, loss_acc);
       }
     };  // e_program
-    if (warp < 4) e_program(std::integral_constant<int, 0>{});
-    else e_program(std::integral_constant<int, 1>{});
+    e_program(warp >> 2);
   } else if (warp == 8) {
     // =================================================================== M: MMA issue
     uint32_t ws = 0, cm = 0;

@@ -255,19 +255,28 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
           mbar_wait(&full[s], (it / WG_STAGES) & 1);
           float4* raw = reinterpret_cast<float4*>(smem + s * WG_STAGE_BYTES);
           float4* lo = reinterpret_cast<float4*>(smem + s * WG_STAGE_BYTES + WG_LO);
+          // The MMA reads the raw fp32 value truncated to tf32 (hi = trunc(x)), so only lo = x - trunc(x) has to
+          // be written: x = hi + lo exactly, lo < 2^-10 |x| and the hardware keeps 11 bits of it, i.e. the pair
+          // represents x to 2^-20 (one-sided).  A round-to-nearest hi would halve that but costs a second
+          // shared-memory write of every operand, and this kernel is bound by shared-memory bandwidth.
+          // Four independent 16-byte loads are in flight per thread (one at a time left the warps waiting on
+          // the shared-memory latency for a fifth of the kernel).
           const int nl = c_stage[l].n_load;
           for (int jl = 0; jl < nl; ++jl) {
             const int f4_begin = c_stage[l].ld[jl].dst / 16, n_f4 = c_stage[l].ld[jl].bytes / 16;
-            for (int j = sid; j < n_f4; j += 256) {
-              const float4 x = raw[f4_begin + j];
-              float4 hi, y;
-              // The MMA reads the raw fp32 value truncated to tf32 (hi = trunc(x)), so only lo = x - trunc(x) has to
-              // be written: x = hi + lo exactly, lo < 2^-10 |x| and the hardware keeps 11 bits of it, i.e. the pair
-              // represents x to 2^-20 (one-sided).  A round-to-nearest hi would halve that but costs a second
-              // shared-memory write of every operand, and this kernel is bound by shared-memory bandwidth.
-              hi.x = tf32_hi(x.x); hi.y = tf32_hi(x.y); hi.z = tf32_hi(x.z); hi.w = tf32_hi(x.w);
-              y.x = x.x - hi.x; y.y = x.y - hi.y; y.z = x.z - hi.z; y.w = x.w - hi.w;
-              lo[f4_begin + j] = y;
+            for (int j0 = sid; j0 < n_f4; j0 += 1024) {
+              float4 x[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (j0 + 256 * u < n_f4) x[u] = raw[f4_begin + j0 + 256 * u];
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (j0 + 256 * u < n_f4) {
+                  float4 y;
+                  y.x = x[u].x - tf32_hi(x[u].x); y.y = x[u].y - tf32_hi(x[u].y);
+                  y.z = x[u].z - tf32_hi(x[u].z); y.w = x[u].w - tf32_hi(x[u].w);
+                  lo[f4_begin + j0 + 256 * u] = y;
+                }
             }
           }
           fence_async_smem();
