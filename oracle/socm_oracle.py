@@ -345,8 +345,11 @@ def socm_loss(
     algorithm: str = "SOCM",
     warm: Optional[WarmStartTable] = None,
     use_stopping_time: bool = False,
+    add_weights: bool = False,
+    y0: Optional[Tensor] = None,
 ):
-    """Faithful restatement of SOC_Solver.loss for algorithm in {SOCM, SOCM_const_M, SOCM_adjoint}
+    """Faithful restatement of SOC_Solver.loss for algorithm in {SOCM, SOCM_const_M, SOCM_adjoint,
+    cross_entropy, variance, log-variance, moment}
     given a finished rollout ``traj`` (the 8-tuple of :func:`rollout`).  The SOCM
     branch keeps the reference's structure on purpose -- reverse-mode ``jacrev`` for
     d/ds M and the materialised (K+1, K+1, B, d, d) integrand -- because this function
@@ -381,6 +384,41 @@ def socm_loss(
         learned = -torch.einsum("ij,...j->...i", st.sigma.t(), gv)
         wanted = -torch.einsum("ij,...j->...i", st.sigma.t(), target)
         obj = torch.sum((learned - wanted) ** 2 * weight.unsqueeze(0).unsqueeze(2)) / (K1 * B)
+        return obj, torch.mean(weight), torch.std(weight)
+
+    if algorithm in ("cross_entropy", "variance", "log-variance", "moment"):   # method.py:751-856
+        # functionals of the per-path sums of a running term that is quadratic in the learned control
+        learned = -torch.einsum("ij,abj->abi", st.sigma.t(), gv)
+        term1 = -(1 / lmbd) * torch.sum(learned[:-1] * controls, dim=2)
+        term2 = (1 / (2 * lmbd)) * torch.sum(learned**2, dim=2)[:-1]
+        det = term1 + term2
+        if algorithm != "cross_entropy":
+            det = det + (-(1 / lmbd) * run_cost(st, states)[:-1])
+        sto = -math.sqrt(1 / lmbd) * torch.sum(learned[:-1] * noises, dim=2)
+        if use_stopping_time and algorithm != "cross_entropy":
+            det = det * stop_ind[:-1]
+            sto = sto * stop_ind[:-1]
+        if use_stopping_time:
+            det_dt, sto_dt = det * frac_dt, sto * torch.sqrt(frac_dt)
+        else:
+            dts = ts[1:] - ts[:-1]
+            det_dt, sto_dt = det * dts.unsqueeze(1), sto * torch.sqrt(dts).unsqueeze(1)
+        det_term, sto_term = torch.sum(det_dt, dim=0), torch.sum(sto_dt, dim=0)
+        if algorithm == "cross_entropy":
+            return torch.mean((det_term + sto_term) * weight), torch.mean(weight), torch.std(weight)
+        g_term = -(1 / lmbd) * term_cost(st, states[-1])
+        if algorithm == "log-variance":
+            sums = det_term + sto_term + g_term
+        elif algorithm == "variance":
+            sums = torch.exp(det_term + sto_term + g_term)
+        else:
+            sums = det_term + sto_term + g_term + y0
+        w2 = weight if add_weights else torch.ones_like(weight)
+        if algorithm == "moment":
+            obj = torch.mean(sums**2 * w2)
+        else:
+            n = sums.shape[0]
+            obj = n / (n - 1) * (torch.mean(sums**2 * w2) - torch.mean(sums * w2) ** 2)
         return obj, torch.mean(weight), torch.std(weight)
 
     if algorithm == "SOCM_adjoint":                                # method.py:722-749

@@ -44,6 +44,10 @@ class _FusedObjective(torch.autograd.Function):
         return (None, lead_grad * gout if ctx.has_lead else None, None, None, *grads)
 
 
+# losses that are functionals of per-path sums of a running term quadratic in the learned control (method.py:751-856)
+PATH_FUNCTIONAL_LOSSES = ("cross_entropy", "log-variance", "variance", "moment")
+
+
 class SOC_Solver(nn.Module):
     noise_type = "diagonal"
     sde_type = "ito"
@@ -128,10 +132,14 @@ class SOC_Solver(nn.Module):
     def loss(self, batch_size, compute_L2_error=False, optimal_control=None, compute_control_objective=False,
              algorithm="SOCM_const_M", add_weights=False, total_n_samples=65536, verbose=False,
              u_warm_start=None, use_warm_start=True, use_stopping_time=False):
+        if algorithm in PATH_FUNCTIONAL_LOSSES:
+            return self._path_functional_loss(batch_size, algorithm, add_weights, bool(use_stopping_time), u_warm_start,
+                                              use_warm_start, compute_L2_error, optimal_control,
+                                              compute_control_objective, total_n_samples)
         if algorithm not in ("SOCM", "SOCM_const_M", "SOCM_adjoint"):
             raise NotImplementedError(
-                f"algorithm {algorithm!r}: SOCM, SOCM_const_M and SOCM_adjoint are on the B200 hot path "
-                "(SURVEY.md section 8; the other losses are 'next' rows)")
+                f"algorithm {algorithm!r}: SOCM, SOCM_const_M, SOCM_adjoint and {PATH_FUNCTIONAL_LOSSES} run on the "
+                "B200 path; SOCM_exp and rel_entropy (back-propagation through the rollout) do not (SURVEY.md section 8f)")
         if compute_L2_error and optimal_control is None:
             raise ValueError("compute_L2_error=True needs optimal_control (a callable (ts, states, t_is_tensor=True))")
         if algorithm == "SOCM_adjoint" and use_stopping_time:
@@ -284,6 +292,107 @@ class SOC_Solver(nn.Module):
             ctrl_mean, ctrl_err, trajectory = self.control_objective(batch_size, total_n_samples=total_n_samples)
         norm_sqd_diff = (l2_sum / ((K + 1) * B)).float() if compute_L2_error else None
         return (objective, norm_sqd_diff, ctrl_mean, ctrl_err, trajectory, mean_w, std_w, stop_indicators)
+
+    # ------------------------------------------------------------------ cross_entropy / (log-)variance / moment
+    def _path_functional_loss(self, batch_size, algorithm, add_weights, stopping, u_warm_start, use_warm_start,
+                              compute_L2_error, optimal_control, compute_control_objective, total_n_samples):
+        """method.py:751-856.  Every one of these objectives is F(S_1..S_B) with the per-path sum
+            S_m = sum_k [ delta_km (-(u.c)/lmbd + |u|^2/(2 lmbd) [- f/lmbd]) - sqrt(delta_km/lmbd) u.eps ]  [- g(x_K)/lmbd],
+        u = u_theta(t_k, x_km) = -sigma^T nabla_V, c / eps = the rollout's controls / noises, delta = dt_k (or the
+        fractional step x stop indicator).  Completing the square,
+            S_m = sum_k (delta/(2 lmbd)) |u - (c + sqrt(lmbd/delta) eps)|^2 + (terms without theta),
+        so dF/dtheta is the gradient of the *importance-weighted squared error K3 already computes*, with path
+        weights a_m = dF/dS_m, point weights delta/(2 lmbd) and target -sigma^{-T}(c + sqrt(lmbd/delta) eps).
+        The value F and a_m come from one extra UNet forward (socm_unet_forward_f32) and reductions over the
+        rollout outputs (torch ops on the GPU); the UNet gradient from the same fused K3 kernels as SOCM."""
+        lib = _lib.load()
+        sde, dev = self.neural_sde, self.x0.device
+        _lib.require_cuda(self.x0, "x0")
+        desc = describe_setting(sde, dev)
+        desc.c_struct.lmbd = float(self.lmbd)
+        d, K, B = desc.d, self.num_steps, int(batch_size)
+        if stopping and not desc.has_stopping:
+            raise _lib.SocmError("use_stopping_time=True needs a setting with a stopping function Phi")
+        ts = self.ts.to(dev).float().contiguous()
+        lam = float(self.lmbd)
+        unet = sde.nabla_V
+        udesc, keep = networks.unet_desc(unet)
+        uparams = networks.unet_parameters(unet)
+        f32 = dict(device=dev, dtype=torch.float32)
+        warm_loss = simulate.resolve_warm_start(_WarmView(u_warm_start), ts) if (u_warm_start and use_warm_start) else None
+        self.launch_count = 0
+        noises_in, self._injected_noise = self._injected_noise, None
+        wsp = simulate.rollout(sde, self.x0.detach().float().reshape(1, d).expand(B, d).contiguous(), ts, self.lmbd,
+                               noises=noises_in, seed=simulate.next_seed(), path_offset=self.path_offset, desc=desc,
+                               force_generic=self.force_generic, force_ffma=self.force_ffma, timer=self._timed)
+        states, noises, controls = wsp.states, wsp.noises, wsp.controls
+        w = torch.exp(wsp.lw[0] + wsp.lw[1] + wsp.lw[2])                       # method.py:258-262
+        sigma = self.sigma.to(dev).float()
+        sig_inv = torch.inverse(sigma)
+        # ---- value: one UNet forward at all (K+1) B points, then reductions (method.py:752-856)
+        gv = unet(torch.cat([ts.reshape(-1, 1, 1).expand(K + 1, B, 1), states], dim=-1))
+        if warm_loss is not None:                                              # method.py:280-287
+            aff = warm_loss.c_loss.unsqueeze(1) + torch.einsum("kij,kbj->kbi", warm_loss.A_loss, states)
+            gv = gv - torch.einsum("ij,kbj->kbi", sig_inv.t(), torch.einsum("ij,kbj->kbi", sig_inv, aff - sde.b(ts, states)))
+        u = -torch.einsum("ij,abj->abi", sigma.t(), gv)[:-1]
+        variance_family = algorithm != "cross_entropy"
+        if stopping:
+            delta = wsp.eff_dt * wsp.stop[:-1] if variance_family else wsp.eff_dt
+        else:
+            delta = (ts[1:] - ts[:-1]).unsqueeze(1).expand(K, B)
+        det = -(1 / lam) * torch.sum(u * controls, dim=2) + (1 / (2 * lam)) * torch.sum(u**2, dim=2)
+        if variance_family:
+            det = det - (1 / lam) * sde.f(ts[0], states)[:-1]
+        sto = -math.sqrt(1 / lam) * torch.sum(u * noises, dim=2)
+        S = torch.sum(det * delta, dim=0) + torch.sum(sto * torch.sqrt(delta), dim=0)
+        if variance_family:
+            S = S - (1 / lam) * sde.g(states[-1])
+        S_leaf = S.detach().requires_grad_(True)
+        w2 = w if add_weights else torch.ones_like(w)
+        if algorithm == "cross_entropy":
+            obj = torch.mean(S_leaf * w)
+        elif algorithm == "moment":
+            obj = torch.mean((S_leaf + self.y0) ** 2 * w2)
+        else:
+            sums = S_leaf if algorithm == "log-variance" else torch.exp(S_leaf)
+            obj = B / (B - 1) * (torch.mean(sums**2 * w2) - torch.mean(sums * w2) ** 2)
+        a_m, = torch.autograd.grad(obj, S_leaf, retain_graph=algorithm == "moment")
+        # ---- gradient: K3 with path weights a_m, point weights delta / (2 lmbd), target -sigma^{-T}(c + sqrt(lmbd/delta) eps)
+        ldt = ((K + 1) * d + 3) // 4 * 4
+        pos = delta > 0
+        tgt = controls + torch.where(pos, torch.sqrt(lam / torch.where(pos, delta, torch.ones_like(delta))),
+                                     torch.zeros_like(delta)).unsqueeze(2) * noises
+        tgt = -torch.einsum("ij,abj->abi", sig_inv.t(), tgt)
+        target = torch.zeros(B, ldt, **f32)
+        target[:, :K * d] = tgt.permute(1, 0, 2).reshape(B, K * d)
+        point_w = torch.zeros(K + 1, B, **f32)
+        point_w[:-1] = delta / (2 * lam)
+        G = torch.zeros(B, ldt, **f32)
+        grad_flat = torch.zeros(int(lib.socm_unet_param_count(udesc)), **f32)
+        loss_sum = torch.zeros(1, device=dev, dtype=torch.float64)
+        loss_ws = torch.empty((int(lib.socm_loss_workspace_bytes(udesc, B, K)) + 3) // 4, **f32)
+        warm_struct = simulate._warm_struct(warm_loss.A_loss, warm_loss.c_loss) if warm_loss is not None else None
+        self._timed("loss_fwdbwd", self._k3_launches(udesc, B, K), lib.socm_unet_loss_fwdbwd_f32,
+                    desc.c_struct, udesc, warm_struct, _lib.ptr(ts), _lib.ptr(states), _lib.ptr(target), ldt,
+                    _lib.ptr(a_m.float().contiguous()), _lib.ptr(point_w), 1.0, B, K, _lib.ptr(G), _lib.ptr(grad_flat),
+                    _lib.ptr(loss_sum), _lib.ptr(loss_ws),
+                    (_lib.LOSS_FORCE_GENERIC if self.force_generic else 0)
+                    | (_lib.LOSS_FORCE_FFMA if self.force_ffma else 0)
+                    | (_lib.LOSS_FORCE_TC if self.force_tc else 0), _lib.stream_ptr())
+        del keep
+        objective = _FusedObjective.apply(obj.detach().float(), None, None, grad_flat, *uparams)
+        if algorithm == "moment":                      # d/d y0 through the torch-side functional
+            objective = objective + (obj - obj.detach())
+        norm_sqd_diff = None
+        if compute_L2_error:
+            if optimal_control is None:
+                raise ValueError("compute_L2_error=True needs optimal_control")
+            norm_sqd_diff = (self._l2_error_sum(sde, unet, optimal_control, warm_loss, ts, states, w) / ((K + 1) * B)).float()
+        ctrl_mean = ctrl_err = trajectory = None
+        if compute_control_objective:
+            ctrl_mean, ctrl_err, trajectory = self.control_objective(batch_size, total_n_samples=total_n_samples)
+        self.last_stats = torch.stack([w.double().sum(), (w.double() ** 2).sum(), wsp.stop.double().sum()])
+        return (objective, norm_sqd_diff, ctrl_mean, ctrl_err, trajectory, torch.mean(w), torch.std(w), wsp.stop)
 
     # ------------------------------------------------------------------ evaluation metric (not on the training path)
     def _l2_error_sum(self, sde, unet, optimal_control, warm_loss, ts, states, w):

@@ -98,6 +98,8 @@ class Golden:
         g = z["gammas"]
         self.gammas = {"gamma": torch.tensor([float(g[0])]), "gamma2": torch.tensor([float(g[1])]),
                        "gamma3": torch.tensor([float(g[2])])}
+        if "solver_y0" in z.files:   # SOC_Solver.y0 (method.py:172), used by the "moment" loss only
+            self.gammas["y0"] = t("solver_y0").reshape(1)
         self.warm = None
         if m["warm"]:
             self.warm = orc.WarmStartTable(t("warm/A_roll"), t("warm/c_roll"), t("warm/A_loss"), t("warm/c_loss"))

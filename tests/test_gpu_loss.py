@@ -13,9 +13,12 @@ DEV = "cuda"
 
 
 def run_product(sde, x0, K, B, lmbd, noises, algo, stopping=False, warm=None, generic=False, chunk=None,
-                ffma=False):
+                ffma=False, y0=None, add_weights=False):
     import soc_matching_b200 as sb
     solver = sb.SOC_Solver(sde, x0.to(DEV), None, T=1.0, num_steps=K, lmbd=lmbd, d=sde.dim, sigma=sde.sigma)
+    if y0 is not None:
+        solver.y0.data.copy_(y0.to(DEV))
+    solver.y0.grad = None
     solver.force_generic = generic
     solver.force_ffma = ffma
     if chunk:
@@ -24,9 +27,9 @@ def run_product(sde, x0, K, B, lmbd, noises, algo, stopping=False, warm=None, ge
         p.grad = None
     solver.inject_noise(noises.to(DEV))
     out = solver.loss(B, algorithm=algo, u_warm_start=sde.u_warm_start if warm is not None else None,
-                      use_warm_start=warm is not None, use_stopping_time=stopping)
+                      use_warm_start=warm is not None, use_stopping_time=stopping, add_weights=add_weights)
     out[0].backward()
-    grads = {}
+    grads = {} if solver.y0.grad is None else {"gam/y0": solver.y0.grad}
     for n, p in sde.nabla_V.named_parameters():
         grads["unet/" + n] = p.grad
     for n, p in sde.M.sigmoid_layers.named_parameters():
@@ -53,12 +56,12 @@ def test_loss_and_grads_match_reference_golden(name):
         sde = make_product_sde(g.setting, g.unet, g.mnet, g.gammas, m["hdims"], m["hdims_M"], DEV,
                                stopping=m["stopping"], warm=g.warm)
         out, grads = run_product(sde, g.x0, m["K"], m["B"], m["lmbd"], g.traj[1], algo, stopping=m["stopping"],
-                                 warm=g.warm)
+                                 warm=g.warm, y0=g.gammas.get("y0"))
         if m["hdims"] == [256, 128, 64]:   # default width runs the tcgen05 kernels: check the FFMA tile path too
             sde2 = make_product_sde(g.setting, g.unet, g.mnet, g.gammas, m["hdims"], m["hdims_M"], DEV,
                                     stopping=m["stopping"], warm=g.warm)
             out2, grads2 = run_product(sde2, g.x0, m["K"], m["B"], m["lmbd"], g.traj[1], algo,
-                                       stopping=m["stopping"], warm=g.warm, ffma=True)
+                                       stopping=m["stopping"], warm=g.warm, ffma=True, y0=g.gammas.get("y0"))
             assert abs(float(out2[0]) - g.scalar(f"{algo}/loss")) <= 1e-4 * abs(g.scalar(f"{algo}/loss"))
             check_grads(grads2, g.grads(algo), gamma_tol=2e-3 if m["stopping"] else None)
         want = g.scalar(f"{algo}/loss")
@@ -78,7 +81,7 @@ CASES = [  # kind, d, K, B, dense sigma
 
 
 @pytest.mark.parametrize("kind,d,K,B,dense", CASES)
-@pytest.mark.parametrize("algo", ["SOCM", "SOCM_const_M", "SOCM_adjoint"])
+@pytest.mark.parametrize("algo", ["SOCM", "SOCM_const_M", "SOCM_adjoint", "cross_entropy", "log-variance"])
 def test_default_width_matches_oracle(kind, d, K, B, dense, algo):
     st = random_setting(kind, d, seed=d + K, dense_sigma=dense)
     hd, hm = [256, 128, 64], [128, 128]
@@ -105,7 +108,10 @@ def test_default_width_matches_oracle(kind, d, K, B, dense, algo):
         sde = make_product_sde(st, unet, mnet, gam, hd, hm, DEV)
         out, grads = run_product(sde, x0, K, B, st.lmbd, noises, algo, generic=(kernel == "generic"),
                                  ffma=(kernel == "ffma"))
-        assert abs(float(out[0]) - float(obj)) <= 1e-4 * abs(float(obj)), (kernel, float(out[0]), float(obj))
+        # cross_entropy = mean(S_m w_m) with S_m of both signs: the value can cancel to ~0, so it is compared on the
+        # scale of its terms (mean weight) rather than relative to itself
+        base = max(abs(float(obj)), float(wm)) if algo == "cross_entropy" else abs(float(obj))
+        assert abs(float(out[0]) - float(obj)) <= 1e-4 * base, (kernel, float(out[0]), float(obj))
         assert abs(float(out[5]) - float(wm)) <= 1e-4 * abs(float(wm))
         check_grads(grads, want)
 

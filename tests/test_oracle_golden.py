@@ -28,7 +28,7 @@ def test_loss_and_grads_match_reference(name):
         mnet = {k: v.clone().requires_grad_(True) for k, v in g.mnet.items()}
         gam = {k: v.clone().requires_grad_(True) for k, v in g.gammas.items()}
         obj, wm, ws = orc.socm_loss(g.setting, unet, mnet, gam, g.ts, g.traj, algorithm=algo,
-                                    warm=g.warm, use_stopping_time=g.meta["stopping"])
+                                    warm=g.warm, use_stopping_time=g.meta["stopping"], y0=gam.get("y0"))
         assert abs(float(obj) - g.scalar(f"{algo}/loss")) <= 2e-6 * abs(g.scalar(f"{algo}/loss"))
         assert abs(float(wm) - g.scalar(f"{algo}/weight_mean")) <= 1e-6 * abs(g.scalar(f"{algo}/weight_mean"))
         assert abs(float(ws) - g.scalar(f"{algo}/weight_std")) <= 1e-5 * abs(g.scalar(f"{algo}/weight_std")) + 1e-12
