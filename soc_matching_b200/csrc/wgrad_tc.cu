@@ -57,6 +57,10 @@ constexpr int WG_STAGES = 2;
 constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;  // + alignment slack + barriers
 constexpr int WG_NT = 320;  // warps 0-3 split + flush, 4 MMA, 5 producer, 6-9 split
 constexpr int WG_PREFETCH = 6;  // stages of L2 prefetch lookahead
+// The tensor core adds into its fp32 accumulator with truncation: 2640 accumulation steps (all 55
+// tiles of a CTA) lose 5e-5 relative, measured against the fp32 FFMA kernel on identical inputs.  The accumulators
+// are therefore flushed (red.global.add: round-to-nearest adds in L2) every WG_SEG tiles = 384 steps (7e-6).
+constexpr int WG_SEG = 8;
 constexpr uint64_t DESC_SW128 = 2ull << 61;  // layout type SWIZZLE_128B
 constexpr int FBB = FB_BYTES;
 
@@ -204,14 +208,15 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
     __syncwarp();
   } else if (warp == 4) {
     // ===================================================== MMA issue
-    uint32_t it = 0;
-    for (int pass = 0; pass < N_PASS; ++pass) {
-      if (my_tiles == 0) break;
-      mbar_wait(acc_empty, (pass & 1) ^ 1);  // the flush warps have drained the previous pass
+    uint32_t it = 0, nf = 0;
+    for (int pass = 0; pass < N_PASS; ++pass)
+    for (int t0 = 0; t0 < my_tiles; t0 += WG_SEG, ++nf) {
+      const int t1 = t0 + WG_SEG < my_tiles ? t0 + WG_SEG : my_tiles;
+      mbar_wait(acc_empty, (nf & 1) ^ 1);  // the flush warps have drained the previous segment
       fence_after_sync();
-      for (int i = 0; i < my_tiles * 4; ++i) {
+      for (int i = t0 * 4; i < t1 * 4; ++i) {
         for (int l = c_pass_stage[pass]; l < c_pass_stage[pass + 1]; ++l, ++it) {
-          const uint32_t first = i == 0 ? 1u : 0u;
+          const uint32_t first = i == t0 * 4 ? 1u : 0u;
           const uint32_t s = it % WG_STAGES;
           mbar_wait(&split[s], (it / WG_STAGES) & 1);
           fence_after_sync();
@@ -245,11 +250,12 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
     const int sid = flusher ? tid : tid - 64;  // 0..255 among the split threads
     const uint32_t lane_t = tm + ((uint32_t)((warp & 3) * 32) << 16);
     const int r = tid & 127;
-    uint32_t it = 0;
-    for (int pass = 0; pass < N_PASS; ++pass) {
-      if (my_tiles == 0) break;
-      // ---- split every stage of this pass: hi = rn_tf32(x) in place, lo = x - hi (second copy)
-      for (int i = 0; i < my_tiles * 4; ++i)
+    uint32_t it = 0, nf = 0;
+    for (int pass = 0; pass < N_PASS; ++pass)
+    for (int t0 = 0; t0 < my_tiles; t0 += WG_SEG, ++nf) {
+      const int t1 = t0 + WG_SEG < my_tiles ? t0 + WG_SEG : my_tiles;
+      // ---- split every stage of this segment: the MMA reads hi = trunc(x) from the raw copy, lo = x - hi
+      for (int i = t0 * 4; i < t1 * 4; ++i)
         for (int l = c_pass_stage[pass]; l < c_pass_stage[pass + 1]; ++l, ++it) {
           const uint32_t s = it % WG_STAGES;
           mbar_wait(&full[s], (it / WG_STAGES) & 1);
@@ -284,7 +290,7 @@ __global__ void __launch_bounds__(WG_NT, 1) wgrad_tc_kernel(const unsigned char*
           if ((tid & 31) == 0) mbar_arrive(&split[s]);
         }
       if (!flusher) continue;
-      mbar_wait(acc_full, pass & 1);
+      mbar_wait(acc_full, nf & 1);
       fence_after_sync();
       for (int o = c_pass_out[pass]; o < c_pass_out[pass + 1]; ++o) {
         const OutDesc od = c_out[o];

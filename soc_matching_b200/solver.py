@@ -67,6 +67,7 @@ class SOC_Solver(nn.Module):
         self.force_generic = False          # tests: run the shape-generic kernels
         self.force_ffma = False             # tests: fp32 FFMA tile kernels instead of the tcgen05 kernels
         self.force_tc = False               # tests: tcgen05 K3 even for small batches
+        self.force_simt_target = False      # tests: fp32 SIMT target GEMMs (K2) next to the tcgen05 K1 / K3
         self._injected_noise = None         # tests: (K, B, d) noise replayed by the next loss() call
         self._pair_grid = None
         self.path_offset = 0                # first global path index of this rank (Philox counter)
@@ -236,7 +237,7 @@ class SOC_Solver(nn.Module):
                 self._timed("target", 1, lib.socm_target_adjoint_f32, desc.c_struct, _lib.ptr(wsp.states), nb, K,
                             float(self.dt), _lib.ptr(target), ldt, stream)
             elif not stopping:
-                if self.force_ffma or self.force_generic:      # fp32 SIMT GEMM
+                if self.force_ffma or self.force_generic or self.force_simt_target:      # fp32 SIMT GEMM
                     self._timed("target", 1, lib.socm_target_gemm_f32, _lib.ptr(L.detach()), _lib.ptr(R), nb, K, d,
                                 ldr, _lib.ptr(target), ldt, stream)
                 else:                                          # tcgen05, 3xTF32 (tape pack + GEMM)
@@ -256,7 +257,7 @@ class SOC_Solver(nn.Module):
                         | (_lib.LOSS_FORCE_FFMA if self.force_ffma else 0)
                         | (_lib.LOSS_FORCE_TC if self.force_tc else 0), stream)
             if L is not None:
-                if self.force_ffma or self.force_generic:      # fp32 SIMT GEMM
+                if self.force_ffma or self.force_generic or self.force_simt_target:      # fp32 SIMT GEMM
                     self._timed("target_bwd", 1, lib.socm_target_gemm_bwd_f32, _lib.ptr(G), _lib.ptr(R), nb, K, d, ldr,
                                 ldt, _lib.ptr(dL), 1, stream)
                 else:                                          # tcgen05, 3xTF32 (2 transposes + GEMM)

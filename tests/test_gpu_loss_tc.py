@@ -230,3 +230,98 @@ def test_tc_k3_general_loss_paths_agree_with_ffma(kind, d, K, B, dense, stopping
     assert abs(l0 - l1) <= 1e-5 * abs(l0), (l0, l1)
     for n in g0:
         assert rel_l2(g1[n], g0[n]) <= 2e-3, (n, rel_l2(g1[n], g0[n]))
+
+
+def test_full_chunk_tc_iteration_agrees_with_fp32_ffma():
+    """BASELINE config 5 at the size of one bench chunk (double_well d=10, K=200, B=75 776 paths = 15.2 M
+    trajectory points, Philox noise): the tcgen05 path (rollout, target GEMMs, K3) against the exact-fp32 FFMA /
+    SIMT path on the same Philox key.  Loss 1e-5; gradient tensors 2e-4: measured 1.2e-4 on the two 64-wide
+    bottleneck layers and <= 5e-5 elsewhere (scripts/path_precision.py attributes it to K3: the SOCM residual
+    nabla_V - target cancels for those layers and amplifies the 3xTF32 chain's 3e-5, see the next test)."""
+    import soc_matching_b200 as sb
+    from soc_matching_b200 import simulate
+    d, K, B = 10, 200, 75776
+    st = random_setting("double_well", d, seed=4)
+    hd, hm = [256, 128, 64], [128, 128]
+    unet, mnet = seeded_unet(d, hd, 5), seeded_mnet(d, hm, 6, 0.1)
+    gam = {"gamma": torch.tensor([6.0]), "gamma2": torch.tensor([1.0]), "gamma3": torch.tensor([1.0])}
+    res = []
+    for ffma in (True, False):
+        torch.manual_seed(1234)
+        simulate._SEED_COUNTER[0] = 77            # same Philox key for both runs
+        sde = make_product_sde(st, unet, mnet, gam, hd, hm, DEV)
+        solver = sb.SOC_Solver(sde, torch.zeros(d, device=DEV), None, T=1.0, num_steps=K, lmbd=1.0, d=d,
+                               sigma=sde.sigma)
+        solver.force_ffma = ffma
+        out = solver.loss(B, algorithm="SOCM")
+        out[0].backward()
+        res.append((float(out[0].detach()), float(out[5]), out[7].clone(),
+                    {n: q.grad.clone() for n, q in sde.named_parameters() if q.grad is not None}))
+        del solver, sde, out
+        torch.cuda.empty_cache()
+    (l0, w0, s0, g0), (l1, w1, s1, g1) = res
+    assert abs(l1 - l0) <= 1e-5 * abs(l0), (l0, l1)
+    assert abs(w1 - w0) <= 1e-5 * abs(w0)
+    assert torch.equal(s0, s1)
+    for n in g0:
+        assert rel_l2(g1[n], g0[n]) <= 2e-4, (n, rel_l2(g1[n], g0[n]))
+
+
+def test_full_chunk_k3_tc_against_fp64_autograd():
+    """K3 on the tensor cores against torch fp64 autograd over all 15.2 M points of a real bench chunk (states of a
+    tcgen05 rollout, double_well d=10, K=200, B=75 776; a well-conditioned random target): every gradient tensor
+    within 1e-4 (measured 2e-5..4.5e-5; the fp32 FFMA kernel: 1e-7..1.3e-5), loss 1e-6.  This is the error of the
+    3xTF32 chain (truncating accumulation, 96 MMAs per 256-wide contraction) plus ReLU-mask flips of
+    pre-activations within ~2e-6 of zero; the weight-gradient accumulators are flushed every 8 tiles."""
+    from soc_matching_b200 import _lib, networks, simulate
+    lib = _lib.load()
+    d, K, B = 10, 200, 75776
+    st_ = random_setting("double_well", d, seed=4)
+    hd, hm = [256, 128, 64], [128, 128]
+    gam = {"gamma": torch.tensor([6.0]), "gamma2": torch.tensor([1.0]), "gamma3": torch.tensor([1.0])}
+    sde = make_product_sde(st_, seeded_unet(d, hd, 5), seeded_mnet(d, hm, 6, 0.1), gam, hd, hm, DEV)
+    ts = torch.linspace(0, 1, K + 1, device=DEV)
+    wsp = simulate.rollout(sde, torch.zeros(B, d, device=DEV), ts, 1.0, seed=99)
+    states, unet = wsp.states, sde.nabla_V
+    udesc, keep = networks.unet_desc(unet)
+    g = torch.Generator(DEV).manual_seed(1)
+    ldt = ((K + 1) * d + 3) // 4 * 4
+    target = 3.0 * torch.randn(B, ldt, device=DEV, generator=g)
+    w = torch.exp(wsp.lw[0] + wsp.lw[1] + wsp.lw[2])
+    st = _lib.Setting()
+    eye, kap = torch.eye(d, device=DEV), torch.ones(d, device=DEV)
+    st.kind, st.d, st.sigma_is_identity, st.lmbd = 2, d, 1, 1.0
+    st.sigma, st.sigma_inv, st.kappa, st.nu = eye.data_ptr(), eye.data_ptr(), kap.data_ptr(), kap.data_ptr()
+    ws = torch.zeros(int(lib.socm_loss_workspace_bytes(udesc, B, K)) // 4 + 1024, device=DEV)
+    scale = 1.0 / ((K + 1) * B)
+    G = torch.zeros(B, ldt, device=DEV)
+    grad = torch.zeros(int(lib.socm_unet_param_count(udesc)), device=DEV)
+    loss = torch.zeros(1, device=DEV, dtype=torch.float64)
+    _lib.check(lib.socm_unet_loss_fwdbwd_f32(st, udesc, None, ts.data_ptr(), states.data_ptr(), target.data_ptr(), ldt,
+                                             w.data_ptr(), None, scale, B, K, G.data_ptr(), grad.data_ptr(),
+                                             loss.data_ptr(), ws.data_ptr(), _lib.LOSS_FORCE_TC, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    P = {n + sfx: getattr(getattr(unet, n)[0], sfx[1:]).detach().double().requires_grad_(True)
+         for n in NAMES for sfx in (".weight", ".bias")}
+    lin = lambda n, v: F.linear(v, P[n + ".weight"], P[n + ".bias"])  # noqa: E731
+    tot = 0.0
+    for i0 in range(0, K + 1, 8):     # fp64 autograd in slabs of 8 grid times
+        i1 = min(K + 1, i0 + 8)
+        tx = torch.cat([ts[i0:i1].double().reshape(-1, 1, 1).expand(i1 - i0, B, 1), states[i0:i1].double()], -1)
+        r1 = torch.relu(lin("down_0", tx)); r2 = torch.relu(lin("down_1", r1)); r3 = torch.relu(lin("down_2", r2))
+        o2 = torch.relu(lin("up_2", r3)) + lin("res_2", r2)
+        o1 = torch.relu(lin("up_1", o2)) + lin("res_1", r1)
+        outv = torch.relu(lin("up_0", o1)) + lin("res_0", tx)
+        tgt = target[:, i0 * d:i1 * d].reshape(B, i1 - i0, d).permute(1, 0, 2).double()
+        L = (((outv - tgt) ** 2).sum(-1) * w.double()[None]).sum() * scale
+        L.backward()
+        tot += float(L.detach())
+    assert abs(float(loss) - tot) <= 1e-6 * abs(tot)
+    off = 0
+    for n in NAMES:
+        for sfx in (".weight", ".bias"):
+            t = P[n + sfx].grad.flatten()
+            got = grad[off:off + t.numel()].double()
+            off += t.numel()
+            assert rel_l2(got, t) <= 1e-4, (n + sfx, rel_l2(got, t))
+    del keep
