@@ -8,6 +8,7 @@ import torch.nn.functional as F
 from helpers import make_product_sde, random_setting, seeded_mnet, seeded_unet
 from soc_matching_b200 import _lib, networks, simulate
 DEV = "cuda"
+torch.manual_seed(0)
 d, K = 10, 200
 B = int(os.environ.get("AB_B", 75776))
 lib = _lib.load()
@@ -25,6 +26,14 @@ g = torch.Generator(DEV).manual_seed(1)
 ldt = ((K + 1) * d + 3) // 4 * 4
 target = 3.0 * torch.randn(B, ldt, device=DEV, generator=g)
 w = torch.exp(wsp.lw[0] + wsp.lw[1] + wsp.lw[2])
+if os.environ.get("REAL_TARGET", "0") == "1":      # the SOCM target of a real iteration (cancelling residual)
+    import soc_matching_b200 as sb
+    solver = sb.SOC_Solver(sde, torch.zeros(d, device=DEV), None, T=1.0, num_steps=K, lmbd=1.0, d=d, sigma=sde.sigma)
+    solver._debug_keep = True
+    solver.loss(B, algorithm="SOCM")
+    states, target, w = solver._debug_last["states"], solver._debug_last["target"], solver._debug_last["w"]
+    del solver
+    torch.cuda.empty_cache()
 st = _lib.Setting()
 eye, kap = torch.eye(d, device=DEV), torch.ones(d, device=DEV)
 st.kind, st.d, st.sigma_is_identity, st.lmbd = 2, d, 1, 1.0

@@ -269,6 +269,8 @@ class SOC_Solver(nn.Module):
                                 ldr, ldt, _lib.ptr(dL), 1, k2b_ws.data_ptr(), stream)
             if compute_L2_error:
                 l2_sum += self._l2_error_sum(sde, unet, optimal_control, warm_loss, ts_f32, wsp.states, wbuf)
+            if getattr(self, "_debug_keep", False):   # scripts/k3_truth.py: inputs of the last K3 call
+                self._debug_last = dict(states=wsp.states.clone(), target=target.clone(), w=wbuf.clone(), ldt=ldt)
             stop_all.append(wsp.stop if B <= chunk else wsp.stop.clone())
         self._injected_noise = None
         del keep
