@@ -202,12 +202,12 @@ CASES = {
     # name: reduced-size versions of the five BASELINE.json configs (+ one full-width net)
     "c1_ou_quadratic_easy": dict(kind="ou_quadratic", d=4, K=12, B=6, hdims=[24, 16, 8], hdims_M=[12, 12],
                                  lmbd=1.0, gamma=2.0, apq=(0.2, 0.2, 0.1), seed=0,
-                                 algorithms=["SOCM", "SOCM_const_M", "SOCM_adjoint", "cross_entropy", "log-variance", "variance", "moment"]),
+                                 algorithms=["SOCM", "SOCM_const_M", "SOCM_exp", "SOCM_adjoint", "cross_entropy", "log-variance", "variance", "moment"]),
     "c1b_ou_quadratic_dense": dict(kind="ou_quadratic", d=3, K=9, B=5, hdims=[16, 12, 8], hdims_M=[10, 10],
                                    lmbd=0.7, gamma=1.5, apq=(0.3, 0.4, 0.2), dense=True, seed=1,
-                                   algorithms=["SOCM", "SOCM_const_M", "SOCM_adjoint", "cross_entropy", "log-variance", "variance", "moment"]),
+                                   algorithms=["SOCM", "SOCM_const_M", "SOCM_exp", "SOCM_adjoint", "cross_entropy", "log-variance", "variance", "moment"]),
     "c2_ou_linear": dict(kind="ou_linear", d=3, K=10, B=5, hdims=[24, 16, 8], hdims_M=[12, 12],
-                         lmbd=1.0, gamma=2.0, seed=2, algorithms=["SOCM", "SOCM_const_M", "SOCM_adjoint"]),
+                         lmbd=1.0, gamma=2.0, seed=2, algorithms=["SOCM", "SOCM_const_M", "SOCM_exp", "SOCM_adjoint"]),
     "c3_ou_quadratic_hard_warm": dict(kind="ou_quadratic", d=3, K=10, B=5, hdims=[24, 16, 8], hdims_M=[12, 12],
                                       lmbd=1.0, gamma=2.0, apq=(1.0, 1.0, 0.5), sf_v=0.1, seed=3,
                                       warm=dict(n_iter=4, lr=2e-4), algorithms=["SOCM", "SOCM_const_M"]),
@@ -216,7 +216,7 @@ CASES = {
                                   algorithms=["SOCM", "cross_entropy", "log-variance", "moment"]),
     "c5_double_well": dict(kind="double_well", d=4, K=100, B=5, hdims=[24, 16, 8], hdims_M=[12, 12],
                            lmbd=1.0, gamma=6.0, seed=5,
-                           algorithms=["SOCM", "SOCM_const_M", "SOCM_adjoint", "cross_entropy", "log-variance", "variance", "moment"]),
+                           algorithms=["SOCM", "SOCM_const_M", "SOCM_exp", "SOCM_adjoint", "cross_entropy", "log-variance", "variance", "moment"]),
     "c5_double_well_fullnet": dict(kind="double_well", d=10, K=100, B=3, hdims=[256, 128, 64], hdims_M=[128, 128],
                                    lmbd=1.0, gamma=6.0, seed=6, param_seed=1234, algorithms=["SOCM", "SOCM_adjoint"]),
 }
@@ -269,11 +269,14 @@ def run_case(ref, name):
         gam = [("gamma", sde.gamma)]
         if c.get("stopping"):
             gam += [("gamma2", sde.gamma2), ("gamma3", sde.gamma3)]
+        if algo == "SOCM_exp":   # main.py:166-169: the decay rate of M_t(s) = exp(-gamma (s - t)) I lives on the solver
+            solver.gamma = torch.nn.Parameter(torch.tensor([float(c["gamma"])]))
         with _ReplayNoise(noises):
             res = solver.loss(B, algorithm=algo, u_warm_start=ws, use_warm_start=bool(ws),
                               use_stopping_time=bool(c.get("stopping")))
         obj = res[0]
-        wanted = params + (pm + gam if algo == "SOCM" else []) + ([("y0", solver.y0)] if algo == "moment" else [])
+        wanted = (params + (pm + gam if algo == "SOCM" else []) + ([("gamma", solver.gamma)] if algo == "SOCM_exp" else [])
+                  + ([("y0", solver.y0)] if algo == "moment" else []))
         grads = torch.autograd.grad(obj, [p for _, p in wanted], allow_unused=True)
         out[f"{algo}/loss"] = obj.detach().numpy()
         out[f"{algo}/weight_mean"] = res[5].detach().numpy()

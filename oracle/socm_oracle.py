@@ -386,6 +386,27 @@ def socm_loss(
         obj = torch.sum((learned - wanted) ** 2 * weight.unsqueeze(0).unsqueeze(2)) / (K1 * B)
         return obj, torch.mean(weight), torch.std(weight)
 
+    if algorithm == "SOCM_exp":                                    # method.py:371-478: M_t(s) = exp(-gamma (s - t)) I
+        gamma = gammas["gamma"]
+        ef = torch.exp(-gamma * ts)
+        ident = torch.eye(d)
+        gb = grad_drift(st, states)[:-1] + gamma * ident
+        term1 = (ef.unsqueeze(1).unsqueeze(2) * grad_run_cost(st, states))[:-1]
+        term2 = ef[:-1].unsqueeze(1).unsqueeze(2) * (-math.sqrt(lmbd) * torch.einsum("abij,abj->abi", gb, eps_t))
+        term3 = ef[:-1].unsqueeze(1).unsqueeze(2) * (-torch.einsum("abij,abj->abi", gb, u_t))
+        terminal = torch.exp(-gamma * (st.T - ts)).unsqueeze(1).unsqueeze(2) * grad_term_cost(st, states[-1]).unsqueeze(0)
+        dts = ts[1:] - ts[:-1]
+
+        def tail(v: Tensor, scale: Tensor) -> Tensor:
+            padded = torch.cat((torch.zeros_like(v[0]).unsqueeze(0), v * scale.unsqueeze(1).unsqueeze(2)), 0)
+            return (1 / ef).unsqueeze(1).unsqueeze(2) * (torch.sum(padded, dim=0).unsqueeze(0) - torch.cumsum(padded, dim=0))
+
+        target = tail(term1, dts) + tail(term2, torch.sqrt(dts)) + tail(term3, dts) + terminal
+        learned = -torch.einsum("ij,...j->...i", st.sigma.t(), gv)
+        wanted = -torch.einsum("ij,...j->...i", st.sigma.t(), target)
+        obj = torch.sum((learned - wanted) ** 2 * weight.unsqueeze(0).unsqueeze(2)) / (K1 * B)
+        return obj, torch.mean(weight), torch.std(weight)
+
     if algorithm in ("cross_entropy", "variance", "log-variance", "moment"):   # method.py:751-856
         # functionals of the per-path sums of a running term that is quadratic in the learned control
         learned = -torch.einsum("ij,abj->abi", st.sigma.t(), gv)

@@ -137,10 +137,12 @@ class SOC_Solver(nn.Module):
             return self._path_functional_loss(batch_size, algorithm, add_weights, bool(use_stopping_time), u_warm_start,
                                               use_warm_start, compute_L2_error, optimal_control,
                                               compute_control_objective, total_n_samples)
-        if algorithm not in ("SOCM", "SOCM_const_M", "SOCM_adjoint"):
+        if algorithm not in ("SOCM", "SOCM_const_M", "SOCM_exp", "SOCM_adjoint"):
             raise NotImplementedError(
-                f"algorithm {algorithm!r}: SOCM, SOCM_const_M, SOCM_adjoint and {PATH_FUNCTIONAL_LOSSES} run on the "
-                "B200 path; SOCM_exp and rel_entropy (back-propagation through the rollout) do not (SURVEY.md section 8f)")
+                f"algorithm {algorithm!r}: SOCM, SOCM_const_M, SOCM_exp, SOCM_adjoint and {PATH_FUNCTIONAL_LOSSES} run on "
+                "the B200 path; rel_entropy (back-propagation through the rollout) does not (SURVEY.md section 8f)")
+        if algorithm == "SOCM_exp" and use_stopping_time:
+            raise NotImplementedError("SOCM_exp ignores stopping times in the reference (method.py:371-478)")
         if compute_L2_error and optimal_control is None:
             raise ValueError("compute_L2_error=True needs optimal_control (a callable (ts, states, t_is_tensor=True))")
         if algorithm == "SOCM_adjoint" and use_stopping_time:
@@ -182,6 +184,17 @@ class SOC_Solver(nn.Module):
             grid = self._grid()
             m_all, dm_all = sde.M.value_and_ds(grid.t, grid.s)
             L = mtable.build_L(m_all, dm_all, grid, ldr)
+            dL = torch.zeros(nrows, ldr, **f32)
+        elif algorithm == "SOCM_exp":
+            # method.py:371-478 is SOCM with M_t(s) = exp(-gamma (s - t)) I and the decay rate a Parameter of the
+            # SOLVER (main.py:166-169): the same table, GEMMs and backward, with an analytic M and d/ds M
+            gamma_p = getattr(self, "gamma", None)
+            if not torch.is_tensor(gamma_p):
+                raise ValueError("SOCM_exp: set solver.gamma = torch.nn.Parameter(torch.tensor([gamma])) (main.py:166-169)")
+            grid = self._grid()
+            decay = torch.exp(-gamma_p.to(dev) * (grid.s - grid.t)).reshape(-1, 1, 1)
+            eye = torch.eye(d, **f32)
+            L = mtable.build_L(decay * eye, (-gamma_p.to(dev)).reshape(1, 1, 1) * decay * eye, grid, ldr)
             dL = torch.zeros(nrows, ldr, **f32)
 
         if self.chunk_paths is None:

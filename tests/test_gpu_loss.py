@@ -19,6 +19,8 @@ def run_product(sde, x0, K, B, lmbd, noises, algo, stopping=False, warm=None, ge
     if y0 is not None:
         solver.y0.data.copy_(y0.to(DEV))
     solver.y0.grad = None
+    if algo == "SOCM_exp":   # main.py:166-169
+        solver.gamma = torch.nn.Parameter(sde.gamma.detach().clone())
     solver.force_generic = generic
     solver.force_ffma = ffma
     if chunk:
@@ -34,7 +36,7 @@ def run_product(sde, x0, K, B, lmbd, noises, algo, stopping=False, warm=None, ge
         grads["unet/" + n] = p.grad
     for n, p in sde.M.sigmoid_layers.named_parameters():
         grads["mnet/sigmoid_layers." + n] = p.grad
-    grads["gam/gamma"] = sde.gamma.grad
+    grads["gam/gamma"] = solver.gamma.grad if algo == "SOCM_exp" else sde.gamma.grad
     if stopping:
         grads["gam/gamma2"], grads["gam/gamma3"] = sde.gamma2.grad, sde.gamma3.grad
     return out, grads
@@ -81,7 +83,7 @@ CASES = [  # kind, d, K, B, dense sigma
 
 
 @pytest.mark.parametrize("kind,d,K,B,dense", CASES)
-@pytest.mark.parametrize("algo", ["SOCM", "SOCM_const_M", "SOCM_adjoint", "cross_entropy", "log-variance"])
+@pytest.mark.parametrize("algo", ["SOCM", "SOCM_const_M", "SOCM_exp", "SOCM_adjoint", "cross_entropy", "log-variance"])
 def test_default_width_matches_oracle(kind, d, K, B, dense, algo):
     st = random_setting(kind, d, seed=d + K, dense_sigma=dense)
     hd, hm = [256, 128, 64], [128, 128]
@@ -101,6 +103,7 @@ def test_default_width_matches_oracle(kind, d, K, B, dense, algo):
     want = {"unet/" + k: v.grad for k, v in pu.items()}
     if algo == "SOCM":
         want.update({"mnet/" + k: v.grad for k, v in pm.items()})
+    if algo in ("SOCM", "SOCM_exp"):
         want["gam/gamma"] = pg["gamma"].grad
     # default dispatch (fp32 FFMA tile K3 below SOCM_LOSS_TC_MIN_POINTS; tcgen05 rollout) and shape-generic;
     # the tcgen05 K3 is covered by tests/test_gpu_loss_tc.py
