@@ -22,8 +22,8 @@ if hasattr(lib, "socm_debug_tc_prof"):
     buf = (ctypes.c_ulonglong * 48)()
     lib.socm_debug_tc_prof(buf)
     steps = K * int(os.environ.get("TILES", 2))
-    names_e = ["xin", "noise", "wait D0", "chunks1", "wait D1", "epi(r2,r3,y2,o2 work)", "wait D2/D3A", "wait D3B", "wait D4A", "epi y1", "wait D0B", "chunks2", "wait D4B", "up_0 loop", "sde", "exchange sync"]
-    names_m = ["loop", "wait XIN", "down0+down_1 issue", "wait R2", "issue(d2,u2,r2)", "wait R3/Y2", "wait O2", "issue up_1", "wait D4A", "issue down0'", "wait Y1", "issue res_1"]
+    names_e = ["xin", "noise", "wait D0", "r1 chunks (down_1 + Wc)", "wait D1", "epi(r2,r3,y2,o2 work)", "wait D2/D3A", "wait D3B", "wait D4A", "-", "-", "y1 chunks (folded up_0)", "wait Y0", "y0 read", "sde", "exchange sync"]
+    names_m = ["loop", "wait XIN", "down0+down_1(+Wc) issue", "wait R2", "issue(d2,u2,r2)", "wait R3/Y2", "wait O2", "issue up_1", "-", "-", "-", "issue up_0 (y1 chunks)"]
     print("E thread 0 (cycles per step):")
     for i, n in enumerate(names_e):
         print(f"  {n:28s} {buf[i] / steps:9.0f}")

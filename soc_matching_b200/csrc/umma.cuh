@@ -164,7 +164,7 @@ __device__ __forceinline__ bool elect_one() {
 // round-to-nearest tf32 (low 13 mantissa bits zero): the "hi" part of the 3xTF32 split; lo = x - hi is exact.
 // Integer form (add half an ulp of the 10-bit mantissa to the magnitude, clear the low bits = ties away
 // from zero, like cvt.rna.tf32.f32): two full-rate ALU ops; the cvt instruction itself was the top stall
-// reason of the epilogue threads (profiles/r1_k3a_stalls.md).
+// reason of the epilogue threads (ncu source view of the first K3a).
 __device__ __forceinline__ float tf32_rn(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
