@@ -150,6 +150,21 @@ int socm_target_const_m_f32(const float* R, int32_t B, int32_t K, int32_t d, int
 int socm_target_adjoint_f32(const socm_setting* st, const float* states, int32_t B, int32_t K, float dt,
                             float* target, int32_t ldt, void* stream);
 
+/* --- optimiser step around the path -------------------------------------------
+ * One launch for the Adam update of every parameter tensor (UNet, M-network, gamma, y0), replacing
+ * torch.optim.Adam.step() [+ zero_grad()] of main.py:174-230, 350-352; torch's single-tensor Adam arithmetic
+ * (no amsgrad, no weight decay), fp32.  `step` is the 1-based step count used for the bias corrections. */
+typedef struct socm_adam_tensor {
+  float* param;
+  float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t n;
+  float lr;
+} socm_adam_tensor;
+int socm_adam_step_f32(const socm_adam_tensor* tensors /* host array */, int32_t n_tensors, double beta1, double beta2,
+                       double eps, int32_t step, int32_t zero_grad, void* stream);
+
 /* --- K3: UNet forward at all (K+1)B points + weighted loss + backward
  *     (replaces method.py:272-287, 692-720 and loss.backward(), main.py:323) -------------
  * loss_sums[0] (fp64) += sum_{i,m} s_im w_m |sigma^T (nabla_V(t_i,x_im) [- sigma^{-T} u_ws] - target_im)|^2 * scale

@@ -14,9 +14,10 @@ from .sde import (DoubleWell, MolecularDynamics, NeuralSDE, OU_Linear, OU_Quadra
                   describe_setting, make_benchmark_sde)
 from .simulate import control_objective, normalization_constant, rollout, stochastic_trajectories  # noqa: F401
 from .solver import SOC_Solver  # noqa: F401
+from .optim import FusedAdam  # noqa: F401
 
 __all__ = [
-    "stochastic_trajectories", "control_objective", "normalization_constant", "rollout", "SOC_Solver", "NeuralSDE",
+    "FusedAdam", "stochastic_trajectories", "control_objective", "normalization_constant", "rollout", "SOC_Solver", "NeuralSDE",
     "FullyConnectedUNet", "SigmoidMLP", "TwoBoundarySigmoidMLP", "WarmStartTable",
     "OU_Quadratic", "OU_Linear", "DoubleWell", "MolecularDynamics", "describe_setting", "make_benchmark_sde",
 ]

@@ -32,6 +32,12 @@ class UNet(C.Structure):
                 ("w", C.c_void_p * 9), ("b", C.c_void_p * 9)]
 
 
+class AdamTensor(C.Structure):
+    """socm_adam_tensor"""
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("n", C.c_int64), ("lr", C.c_float)]
+
+
 class WarmTable(C.Structure):
     """socm_warm_table"""
     _fields_ = [("A", C.c_void_p), ("c", C.c_void_p)]
@@ -58,6 +64,7 @@ PROTOTYPES = {
     "socm_target_gemm_bwd_tc_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp]),
     "socm_target_const_m_f32": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "socm_target_adjoint_f32": (C.c_int, [C.POINTER(Setting), _vp, _i32, _i32, _f32, _vp, _i32, _vp]),
+    "socm_adam_step_f32": (C.c_int, [C.POINTER(AdamTensor), _i32, C.c_double, C.c_double, C.c_double, _i32, _i32, _vp]),
     "socm_loss_workspace_bytes": (_i64, [C.POINTER(UNet), _i32, _i32]),
     "socm_unet_param_count": (_i64, [C.POINTER(UNet)]),
     "socm_unet_loss_fwdbwd_f32": (C.c_int, [C.POINTER(Setting), C.POINTER(UNet), C.POINTER(WarmTable), _vp, _vp,
