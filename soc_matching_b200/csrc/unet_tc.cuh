@@ -7,12 +7,12 @@
 //   * the activations (A operand) are written back to TMEM by the epilogue threads
 //     (thread e <-> point e <-> TMEM lane e: no cross-thread traffic) and read by the next layer
 //     straight from TMEM (tcgen05.mma with A in tensor memory);
-//   * the two 256-wide activations (r1 = relu(down_0 x) and its re-use by res_1) do not fit next
-//     to the accumulators, so they are produced in 32-feature chunks into a double-buffered
-//     shared-memory A operand and consumed chunk by chunk;
+//   * the two 256-wide activations (r1 = relu(down_0 x) feeding down_1 and the folded Wc, y1 = relu(up_1 o2)
+//     feeding the folded up_0) do not fit next to the accumulators, so they are produced in 32-feature
+//     chunks into a double-buffered shared-memory A operand and consumed chunk by chunk;
 //   * the weights (B operand, K-major = nn.Linear's own [out][in] layout) are streamed from L2
 //     every step as a fixed tape of 32 KB slots by cp.async.bulk into a 3-stage ring
-//     (1.3 MB per 128 points and step; measured 132 GB/s per SM, see scripts/umma_probe.cu).
+//     (0.8 MB per 128 points and evaluation; measured 132 GB/s per SM, see scripts/umma_probe.cu).
 //
 // Precision.  kind::tf32 truncates its fp32 inputs to 10 mantissa bits, so every product is
 // issued three times on split operands  x = hi + lo,  hi = rn_tf32(x), lo = x - hi (exact):
@@ -21,10 +21,11 @@
 // activations by the epilogue threads.
 //
 // TMEM column map (512 columns), forward pass:
-//   [0,256)    D0 = down_0 pre-activation (chunk source)  ->  r2 hi|lo  ->  o2 hi|lo  ->  D0 again
+//   [0,256)    D0 = down_0 pre-activation (chunk source)  ->  r2 hi|lo  ->  o2 hi|lo  ->  [0,NY) W_u0 y1 acc
 //   [256,384)  D1 = down_1 acc  -> D2 = down_2 acc [256,320) -> D3 = up_2/res_2 acc
+//   [384,400)  Wc r1 acc (joint MMA with down_1; read out before r3 is written)
 //   [384,512)  r3 hi|lo
-//   [256,512)  D4 = up_1/res_1 acc (after D3 and r3 are dead)
+//   [256,512)  D4 = up_1 acc (after D3 and r3 are dead)
 #pragma once
 #include "common.cuh"
 #include "umma.cuh"
