@@ -50,7 +50,7 @@ constexpr int SM_SMALL = SM_XIN + MAX_KIN * 1024;
 enum Bar {
   W_FULL = 0, W_EMPTY = W_FULL + NSTAGE, CH_FULL = W_EMPTY + NSTAGE, CH_EMPTY = CH_FULL + 2,
   // forward, one completion per tile each
-  XIN_FULL = CH_EMPTY + 2, D0_FULL, D1_FULL, R2_FULL, D2_FULL, R3_FULL, D3A_FULL, Y2_FULL, D3B_FULL, O2_FULL,
+  XIN_FULL = CH_EMPTY + 2, D0_FULL, D1_FULL, R2_FULL, D2_FULL, R3_FULL, D3A_FULL, D3B_FULL, O2_FULL,
   D4A_FULL, Y0_FULL,
   // backward
   DY0_FULL, BD0_FULL, BDO2_FULL, BO2_FULL, BR2A_FULL, BY2_FULL, BD3_FULL, BZ3_FULL, BR2B_FULL, BZ2_FULL,
@@ -62,7 +62,7 @@ enum Bar {
   R2H_FULL, BO2H_FULL, BY2H_FULL, N_BARS
 };
 constexpr int NT = 320, NE = 256;
-constexpr uint32_t C_SA = 0, C_D1 = 256, C_D2 = 256, C_D3 = 256, C_R3 = 384, C_D4 = 256;
+constexpr uint32_t C_SA = 0, C_D1 = 256, C_D2 = 256, C_D3 = 256, C_D3R = 384, C_D4 = 256;
 constexpr uint32_t C_DO2 = 256, C_DR2 = 384, C_DR3 = 256, C_DR1 = 256;
 constexpr uint32_t C_Y0P = 384, C_Y0 = 0;
 static_assert(C_Y0P == C_D1 + H1, "Wc r1 must sit right behind the down_1 accumulator (joint MMA)");  // folded last layer: Wc r1 (next to down_1) and W_u0 y1 (after up_1)
@@ -108,16 +108,6 @@ __device__ __forceinline__ void apply_bits(float* v, uint32_t m) {
 #pragma unroll
   for (int j = 0; j < NV; ++j) v[j] = ((m >> j) & 1u) ? v[j] : 0.f;
 }
-__device__ __forceinline__ void store_split16(uint32_t a_hi, uint32_t a_lo, const float* v) {
-  uint32_t h[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) h[j] = __float_as_uint(tf32_rn(v[j]));
-  tmem_st16(a_hi, h);
-#pragma unroll
-  for (int j = 0; j < 16; ++j) h[j] = __float_as_uint(v[j] - __uint_as_float(h[j]));
-  tmem_st16(a_lo, h);
-}
-
 template <int KIN>
 __global__ void __launch_bounds__(k3::NT, 1)
     loss_tc_kernel(LossArgs a, const unsigned char* __restrict__ tape, const float* __restrict__ small_g,
@@ -153,9 +143,9 @@ __global__ void __launch_bounds__(k3::NT, 1)
     }
     mbar_init(&bars[XIN_FULL], TP / 32);
     mbar_init(&bars[DY0_FULL], TP / 32);
-    const int e2m[] = {R2_FULL, R3_FULL, Y2_FULL, O2_FULL, BO2_FULL, BY2_FULL, BZ3_FULL, BZ2_FULL,
+    const int e2m[] = {R2_FULL, R3_FULL, O2_FULL, BO2_FULL, BY2_FULL, BZ3_FULL, BZ2_FULL,
                        R2H_FULL, BO2H_FULL, BY2H_FULL};
-    for (int i = 0; i < 11; ++i) mbar_init(&bars[e2m[i]], NE / 32);
+    for (int i = 0; i < 10; ++i) mbar_init(&bars[e2m[i]], NE / 32);
     const int m2e[] = {D0_FULL, D1_FULL, D2_FULL, D3A_FULL, D3B_FULL, D4A_FULL, Y0_FULL, BD0_FULL,
                        BDO2_FULL, BR2A_FULL, BD3_FULL, BR2B_FULL, BD1B_FULL};
     for (int i = 0; i < 13; ++i) mbar_init(&bars[m2e[i]], 1);
@@ -298,7 +288,7 @@ __global__ void __launch_bounds__(k3::NT, 1)
         tmem_wait_st();
         fence_before_sync();
         warp_arrive(&bars[R2_FULL]);
-        // ---- F3: r3
+        // ---- F3: r3 -> shared-memory A operand (features [32h, 32h+32) = chunk buffer h), mask, scratch
         K3P_MARK;
         mbar_wait(&bars[D2_FULL], ph);
         K3P_MARK;
@@ -309,44 +299,34 @@ __global__ void __launch_bounds__(k3::NT, 1)
           tmem_wait_ld();
           bias_relu32(v, sm_small + so.b_d2 + 32 * h);
           m_r3 = positive_bits<32>(v);
-          store_split32(lane_t + C_R3 + 32 * h, lane_t + C_R3 + 64 + 32 * h, v);
+          store_chunk32(smem + SM_CHUNK + h * CHUNK_BYTES, p, v);
           store_fb32(sq + (FB_R3 + h) * FB_BYTES, ro, v);
         }
-        tmem_wait_st();
         fence_before_sync();
+        fence_async_smem();
         warp_arrive(&bars[R3_FULL]);
-        // ---- F4: y2 = relu(D3 + b_u2) in place
+        // ---- F5: o2 = relu(D3 + b_u2) + D3R + b_r2 (up_2 and res_2 have both finished) -> A operand, mask, scratch
         K3P_MARK;
         mbar_wait(&bars[D3A_FULL], ph);
-        K3P_MARK;
-        fence_after_sync();
-#pragma unroll 1
-        for (int i = 0; i < 2; ++i) {
-          const int cb = 2 * i + h;  // iteration 0 covers columns [0,64), iteration 1 [64,128)
-          float v[32];
-          tmem_ld32(lane_t + C_D3 + 32 * cb, reinterpret_cast<uint32_t*>(v));
-          tmem_wait_ld();
-          bias_relu32(v, sm_small + so.b_u2 + 32 * cb);
-          m_y2 |= (uint64_t)positive_bits<32>(v) << (32 * i);
-          tmem_st32(lane_t + C_D3 + 32 * cb, reinterpret_cast<const uint32_t*>(v));
-        }
-        tmem_wait_st();
-        fence_before_sync();
-        warp_arrive(&bars[Y2_FULL]);
-        // ---- F5: o2
-        K3P_MARK;
         mbar_wait(&bars[D3B_FULL], ph);
         K3P_MARK;
         fence_after_sync();
 #pragma unroll 1
-        for (int i = 0; i < 2; ++i) {
-          const int cb = 2 * i + h;  // iteration 0 covers columns [0,64), iteration 1 [64,128)
-          float v[32];
-          tmem_ld32(lane_t + C_D3 + 32 * cb, reinterpret_cast<uint32_t*>(v));
+        for (int ii = 0; ii < 4; ++ii) {
+          const int i = ii >> 1, hh = ii & 1;
+          const int cb = 2 * i + h;  // iteration i covers columns [64 i, 64 i + 64) of both halves
+          const int c0 = 32 * cb + 16 * hh;
+          float y[16], rr[16];
+          tmem_ld16(lane_t + C_D3 + c0, reinterpret_cast<uint32_t*>(y));
+          tmem_ld16(lane_t + C_D3R + c0, reinterpret_cast<uint32_t*>(rr));
           tmem_wait_ld();
-          bias32(v, sm_small + so.b_r2 + 32 * cb);
-          store_split32(lane_t + C_SA + 32 * cb, lane_t + C_SA + 128 + 32 * cb, v);
-          store_fb32(sq + (FB_O2 + cb) * FB_BYTES, ro, v);
+          bias_relu16(y, sm_small + so.b_u2 + c0);
+          m_y2 |= (uint64_t)positive_bits<16>(y) << (32 * i + 16 * hh);
+          const float* br = sm_small + so.b_r2 + c0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) y[j] += rr[j] + br[j];
+          store_split16(lane_t + C_SA + c0, lane_t + C_SA + 128 + c0, y);
+          store_fb16(sq + (FB_O2 + cb) * FB_BYTES, ro, 16 * hh, y);
         }
         tmem_wait_st();
         fence_before_sync();
@@ -656,22 +636,21 @@ __global__ void __launch_bounds__(k3::NT, 1)
         release_w();
       }
       signal(D2_FULL);
-      wait_e(R3_FULL, ph);          // up_2: A = r3
-      for (int j = 0; j < 2; ++j) {
+      for (int j = 0; j < 4; ++j) {  // res_2 right behind down_2: A = r2, its own accumulator D3R
         const uint32_t wb = wait_w();
-        if (elect_one()) issue_block_ts<H1, 32>(tm + C_D3, tm + C_R3 + 32 * j, tm + C_R3 + 64 + 32 * j, wb, j == 0);
-        __syncwarp();
-        release_w();
-      }
-      signal(D3A_FULL);
-      wait_e(Y2_FULL, ph);          // res_2 on top of relu(y2): A = r2
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t wb = wait_w();
-        if (elect_one()) issue_block_ts<H1, 32>(tm + C_D3, tm + C_SA + 32 * j, tm + C_SA + 128 + 32 * j, wb, false);
+        if (elect_one()) issue_block_ts<H1, 32>(tm + C_D3R, tm + C_SA + 32 * j, tm + C_SA + 128 + 32 * j, wb, j == 0);
         __syncwarp();
         release_w();
       }
       signal(D3B_FULL);
+      wait_e(R3_FULL, ph);          // up_2: A = r3 in the two shared-memory chunk buffers
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t wb = wait_w();
+        if (elect_one()) issue_block_ss<H1, 32>(tm + C_D3, chunk_s + j * CHUNK_BYTES, CHUNK_HALF, wb, j == 0);
+        __syncwarp();
+        release_w();
+      }
+      signal(D3A_FULL);
       wait_e(O2_FULL, ph);          // up_1: A = o2
       for (int j = 0; j < 8; ++j) {
         const uint32_t wb = wait_w();

@@ -88,7 +88,7 @@ constexpr int SM_XIN = SM_CHUNK + 2 * CHUNK_BYTES;
 constexpr int SM_SMALL = SM_XIN + MAX_KIN * 1024;  // xin: hi + lo, 128 x kin floats each
 enum Bar {
   W_FULL = 0, W_EMPTY = W_FULL + NSTAGE, CH_FULL = W_EMPTY + NSTAGE, CH_EMPTY = CH_FULL + 2,
-  XIN_FULL = CH_EMPTY + 2, D0_FULL, D1_FULL, R2_FULL, D2_FULL, R3_FULL, D3A_FULL, Y2_FULL, D3B_FULL, O2_FULL,
+  XIN_FULL = CH_EMPTY + 2, D0_FULL, D1_FULL, R2_FULL, D2_FULL, R3_FULL, D3A_FULL, D3B_FULL, O2_FULL,
   D4A_FULL, Y0_FULL,
   R2H_FULL,  // first column half of r2 is ready: down_2 starts on its K block 0 while the second half is written
   N_BARS
@@ -110,7 +110,7 @@ __device__ unsigned long long g_tc_prof[48];
 #define PROF_FLUSH(base, cond)
 #endif
 // TMEM columns
-constexpr uint32_t C_SA = 0, C_D1 = 256, C_D2 = 256, C_D3 = 256, C_R3 = 384, C_D4 = 256;
+constexpr uint32_t C_SA = 0, C_D1 = 256, C_D2 = 256, C_D3 = 256, C_D3R = 384, C_D4 = 256;
 // folded last layer (unet_tc.cuh): C_Y0P = Wc r1, accumulated next to down_1 and read out before r3 is
 // written there; C_Y0 = W_u0 y1, accumulated over the y1 chunks once up_1 has consumed o2.
 constexpr uint32_t C_Y0P = 384, C_Y0 = 0;
@@ -170,8 +170,8 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
       mbar_init(&bars[CH_EMPTY + b], 1);
     }
     mbar_init(&bars[XIN_FULL], TP / 32);
-    const int e2m[] = {R2_FULL, R3_FULL, Y2_FULL, O2_FULL, R2H_FULL};
-    for (int i = 0; i < 5; ++i) mbar_init(&bars[e2m[i]], NE / 32);
+    const int e2m[] = {R2_FULL, R3_FULL, O2_FULL, R2H_FULL};
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[e2m[i]], NE / 32);
     const int m2e[] = {D0_FULL, D1_FULL, D2_FULL, D3A_FULL, D3B_FULL, D4A_FULL, Y0_FULL};
     for (int i = 0; i < 7; ++i) mbar_init(&bars[m2e[i]], 1);
     mbar_init_fence();
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
         fence_before_sync();
         warp_arrive(&bars[R2_FULL]);
         PROF_MARK(5);
-        // ---- E3: r3 = relu(D2 + b) -> [384,448) hi, [448,512) lo   (32 columns per half)
+        // ---- E3: r3 = relu(D2 + b) -> shared-memory A operand: features [32h, 32h+32) = chunk buffer h
         mbar_wait(&bars[D2_FULL], ph);
         PROF_MARK(6);
         fence_after_sync();
@@ -316,40 +316,29 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
           tmem_ld32(lane_t + C_D2 + 32 * h, reinterpret_cast<uint32_t*>(v));
           tmem_wait_ld();
           bias_relu32(v, sm_small + so.b_d2 + 32 * h);
-          store_split32(lane_t + C_R3 + 32 * h, lane_t + C_R3 + 64 + 32 * h, v);
+          store_chunk32(smem + SM_CHUNK + h * CHUNK_BYTES, p, v);
         }
-        tmem_wait_st();
         fence_before_sync();
+        fence_async_smem();
         warp_arrive(&bars[R3_FULL]);
         PROF_MARK(5);
-        // ---- E4: y2 = relu(D3 + b_u2) in place
+        // ---- E5: o2 = relu(D3 + b_u2) + D3R + b_r2 -> TMEM A operand [0,128) hi, [128,256) lo  (up_2 and res_2 done)
         mbar_wait(&bars[D3A_FULL], ph);
-        PROF_MARK(6);
-        fence_after_sync();
-#pragma unroll 1
-        for (int cb = 2 * h; cb < 2 * h + 2; ++cb) {
-          float v[32];
-          tmem_ld32(lane_t + C_D3 + 32 * cb, reinterpret_cast<uint32_t*>(v));
-          tmem_wait_ld();
-          bias_relu32(v, sm_small + so.b_u2 + 32 * cb);
-          tmem_st32(lane_t + C_D3 + 32 * cb, reinterpret_cast<const uint32_t*>(v));
-        }
-        tmem_wait_st();
-        fence_before_sync();
-        warp_arrive(&bars[Y2_FULL]);
-        PROF_MARK(5);
-        // ---- E5: o2 = D3 + b_r2 -> TMEM A operand [0,128) hi, [128,256) lo
         mbar_wait(&bars[D3B_FULL], ph);
         PROF_MARK(7);
         fence_after_sync();
 #pragma unroll 1
-        for (int i = 0; i < 2; ++i) {
-          const int cb = 2 * i + h;  // iteration 0 covers columns [0,64) = K blocks 0..3 of up_1
-          float v[32];
-          tmem_ld32(lane_t + C_D3 + 32 * cb, reinterpret_cast<uint32_t*>(v));
+        for (int i = 0; i < 4; ++i) {
+          const int c0 = 64 * (i >> 1) + 32 * h + 16 * (i & 1);  // iterations 0, 1 cover columns [0,64) of both halves
+          float y[16], rr[16];
+          tmem_ld16(lane_t + C_D3 + c0, reinterpret_cast<uint32_t*>(y));
+          tmem_ld16(lane_t + C_D3R + c0, reinterpret_cast<uint32_t*>(rr));
           tmem_wait_ld();
-          bias32(v, sm_small + so.b_r2 + 32 * cb);
-          store_split32(lane_t + C_SA + 32 * cb, lane_t + C_SA + 128 + 32 * cb, v);
+          const float* bu = sm_small + so.b_u2 + c0;
+          const float* br = sm_small + so.b_r2 + c0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j] + bu[j], 0.f) + (rr[j] + br[j]);
+          store_split16(lane_t + C_SA + c0, lane_t + C_SA + 128 + c0, y);
         }
         tmem_wait_st();
         fence_before_sync();
@@ -536,30 +525,27 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
       if (elect_one()) commit(&bars[D2_FULL]);
       __syncwarp();
       PROF_MARK(4);
-      // ---- M3: up_2, A = r3 (TMEM), 2 blocks of K = 32
+      // ---- M3: res_2 right behind down_2 (A = r2 in TMEM, own accumulator D3R), 4 blocks of K = 32
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t wb = wait_w();
+        if (elect_one()) issue_block_ts<H1, 32>(tm + C_D3R, tm + C_SA + 32 * j, tm + C_SA + 128 + 32 * j, wb, j == 0);
+        __syncwarp();
+        release_w();
+      }
+      if (elect_one()) commit(&bars[D3B_FULL]);
+      __syncwarp();
+      PROF_MARK(4);
+      // ---- M4: up_2, A = r3 in the two shared-memory chunk buffers, 2 blocks of K = 32
       mbar_wait(&bars[R3_FULL], ph);
       PROF_MARK(5);
       fence_after_sync();
       for (int j = 0; j < 2; ++j) {
         const uint32_t wb = wait_w();
-        if (elect_one()) issue_block_ts<H1, 32>(tm + C_D3, tm + C_R3 + 32 * j, tm + C_R3 + 64 + 32 * j, wb, j == 0);
+        if (elect_one()) issue_block_ss<H1, 32>(tm + C_D3, chunk_s + j * CHUNK_BYTES, CHUNK_HALF, wb, j == 0);
         __syncwarp();
         release_w();
       }
       if (elect_one()) commit(&bars[D3A_FULL]);
-      __syncwarp();
-      PROF_MARK(4);
-      // ---- M4: res_2 on top of relu(y2), A = r2 (TMEM), 4 blocks of K = 32
-      mbar_wait(&bars[Y2_FULL], ph);
-      PROF_MARK(5);
-      fence_after_sync();
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t wb = wait_w();
-        if (elect_one()) issue_block_ts<H1, 32>(tm + C_D3, tm + C_SA + 32 * j, tm + C_SA + 128 + 32 * j, wb, false);
-        __syncwarp();
-        release_w();
-      }
-      if (elect_one()) commit(&bars[D3B_FULL]);
       __syncwarp();
       PROF_MARK(4);
       // ---- M5: up_1, A = o2 (TMEM), 8 blocks of K = 16

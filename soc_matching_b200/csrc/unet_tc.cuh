@@ -22,10 +22,12 @@
 //
 // TMEM column map (512 columns), forward pass:
 //   [0,256)    D0 = down_0 pre-activation (chunk source)  ->  r2 hi|lo  ->  o2 hi|lo  ->  [0,NY) W_u0 y1 acc
-//   [256,384)  D1 = down_1 acc  -> D2 = down_2 acc [256,320) -> D3 = up_2/res_2 acc
-//   [384,400)  Wc r1 acc (joint MMA with down_1; read out before r3 is written)
-//   [384,512)  r3 hi|lo
-//   [256,512)  D4 = up_1 acc (after D3 and r3 are dead)
+//   [256,384)  D1 = down_1 acc  -> D2 = down_2 acc [256,320) -> D3 = up_2 acc
+//   [384,400)  Wc r1 acc (joint MMA with down_1; read out before res_2 writes there)
+//   [384,512)  D3R = res_2 acc: res_2 runs right behind down_2, under the r3 epilogue and up_2, instead of after a
+//              separate relu(y2) pass; r3 (64 features, hi|lo = 64 KB) is an A operand in the two shared-memory
+//              chunk buffers, which are idle between the r1 and the y1 chunks
+//   [256,512)  D4 = up_1 acc (after D3 and D3R are dead)
 #pragma once
 #include "common.cuh"
 #include "umma.cuh"
@@ -59,7 +61,7 @@ __host__ __device__ inline int u0_slots(int d) { return ny_of(d) == 16 ? 1 : 2; 
 //     d_r1 += Wc^T d_y0 (K = d),   dW_r1 = W_u0^T S,   dW_u0 = d_y0^T y1 + S W_r1^T + (sum d_y0) b_r1^T,   S = d_y0^T r1.
 //
 // ---------------------------------------------------------------- weight tapes
-// forward slots: [down_0 x S] [down_1 x 8, each followed by its Wc block] [down_2 x 2] [up_2 x 2] [res_2 x 4]
+// forward slots: [down_0 x S] [down_1 x 8, each followed by its Wc block] [down_2 x 2] [res_2 x 4] [up_2 x 2]
 //                [up_1 x 8] [up_0 x U: 8 K-chunks of 32, several per slot]
 // backward slots (W^T blocks): [up_0^T x S] [up_1^T x 8] [res_2^T x 4] [up_2^T x 2] [down_2^T x 2] [down_1^T x 8] [Wc^T x S]
 struct SlotDesc {
@@ -95,10 +97,11 @@ __host__ __device__ inline PackItem fwd_item(int d, int i) {
   i -= 8;
   if (i < 2) return PackItem{S + 8 + i, 0, SlotDesc{2, 0, H2, 64 * i, 64, H1, 0, H1, NOLIM, 0, 0}};
   i -= 2;
-  if (i < 2) return PackItem{S + 10 + i, 0, SlotDesc{6, 0, H1, 32 * i, 32, H2, 0, H2, NOLIM, 0, 0}};
-  i -= 2;
-  if (i < 4) return PackItem{S + 12 + i, 0, SlotDesc{5, 0, H1, 32 * i, 32, H1, 0, H1, NOLIM, 0, 0}};
+  // res_2 is issued right behind down_2 (both read r2; it has its own accumulator), up_2 after the r3 epilogue
+  if (i < 4) return PackItem{S + 10 + i, 0, SlotDesc{5, 0, H1, 32 * i, 32, H1, 0, H1, NOLIM, 0, 0}};
   i -= 4;
+  if (i < 2) return PackItem{S + 14 + i, 0, SlotDesc{6, 0, H1, 32 * i, 32, H2, 0, H2, NOLIM, 0, 0}};
+  i -= 2;
   if (i < 8) return PackItem{S + 16 + i, 0, SlotDesc{7, 0, H0, 16 * i, 16, H1, 0, H1, NOLIM, 0, 0}};
   i -= 8;
   const int bps = MAIN_BYTES / (NY * 256);  // up_0 K-chunks per slot (8 or 4)
@@ -249,6 +252,15 @@ __device__ __forceinline__ void store_split32(uint32_t a_hi, uint32_t a_lo, cons
 #pragma unroll
   for (int j = 0; j < 32; ++j) h[j] = __float_as_uint(v[j] - __uint_as_float(h[j]));
   umma::tmem_st32(a_lo, h);
+}
+__device__ __forceinline__ void store_split16(uint32_t a_hi, uint32_t a_lo, const float* v) {
+  uint32_t h[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) h[j] = __float_as_uint(umma::tf32_rn(v[j]));
+  umma::tmem_st16(a_hi, h);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) h[j] = __float_as_uint(v[j] - __uint_as_float(h[j]));
+  umma::tmem_st16(a_lo, h);
 }
 // shared-memory A operand chunk (32 features of point p): hi at chunk, lo at chunk + CHUNK_HALF
 __device__ __forceinline__ void store_chunk32(unsigned char* chunk, int p, const float* v) {
