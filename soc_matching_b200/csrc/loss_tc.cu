@@ -331,6 +331,27 @@ __global__ void __launch_bounds__(k3::NT, 1)
         tmem_wait_st();
         fence_before_sync();
         warp_arrive(&bars[O2_FULL]);
+        // up_1 runs for ~6k cycles now: the owner half evaluates res_0 [t, x] meanwhile (it depends on the state only)
+        float ar[KIN];
+#pragma unroll
+        for (int j = 0; j < KIN; ++j) ar[j] = 0.f;
+        if (h == 0) {
+          const float tk = __ldg(a.ts + ti);
+#pragma unroll
+          for (int j = 0; j < KIN; ++j) {
+            const float4* wr = reinterpret_cast<const float4*>(sm_small + so.r0 + j * KIN);
+            float acc_r = sm_small[so.b_r0 + j];
+#pragma unroll
+            for (int c4 = 0; c4 < KIN / 4; ++c4) {
+              const float4 w = wr[c4];
+              acc_r = fmaf(w.x, c4 == 0 ? tk : x[4 * c4 - 1], acc_r);
+              acc_r = fmaf(w.y, x[4 * c4], acc_r);
+              acc_r = fmaf(w.z, x[4 * c4 + 1], acc_r);
+              acc_r = fmaf(w.w, x[4 * c4 + 2], acc_r);
+            }
+            ar[j] = acc_r;
+          }
+        }
         // ---- F6: y1 = relu(D4 + b_u1) -> A chunks of the folded up_0 (+ mask, + scratch)
         K3P_MARK;
         mbar_wait(&bars[D4A_FULL], ph);
@@ -360,15 +381,10 @@ __global__ void __launch_bounds__(k3::NT, 1)
         // ---- loss (owners): nabla_V, d loss / d nabla_V, G; d_y0 operand for the backward pass
         if (h == 0) {
           float gv[KIN], y0[KIN], dv[KIN];
-          const float tk = __ldg(a.ts + ti);
 #pragma unroll
           for (int j = 0; j < KIN; ++j) {
-            const float* wr = sm_small + so.r0 + j * KIN;
-            float ar = fmaf(wr[0], tk, sm_small[so.b_r0 + j]);
-#pragma unroll
-            for (int c = 1; c < KIN; ++c) ar = fmaf(wr[c], x[c - 1], ar);
             y0[j] = au[j] + sm_small[so.bc + j];
-            gv[j] = fmaxf(y0[j], 0.f) + ar;
+            gv[j] = fmaxf(y0[j], 0.f) + ar[j];
             dv[j] = 0.f;
           }
           if (live) {

@@ -349,6 +349,28 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
 #pragma unroll
         for (int j = 0; j < KIN; ++j) eps[j] = 0.f;
         if (h == 1 && live) draw_noise_reg<KIN>(a, m, k, eps);
+        // ... and the owner half evaluates res_0 [t, x] (it depends on the state only), which takes the d x (d+1)
+        // mat-vec out of the serial tail of the step
+        float ar[KIN];
+#pragma unroll
+        for (int j = 0; j < KIN; ++j) ar[j] = 0.f;
+        if (h == 0) {
+          const float tk = __ldg(a.step_tab + 4 * K + k);
+#pragma unroll
+          for (int j = 0; j < KIN; ++j) {  // lanes >= d come out as exact zeros (zero-padded parameters)
+            const float4* wr = reinterpret_cast<const float4*>(sm_small + so.r0 + j * KIN);
+            float acc_r = sm_small[so.b_r0 + j];
+#pragma unroll
+            for (int c4 = 0; c4 < KIN / 4; ++c4) {
+              const float4 w = wr[c4];
+              acc_r = fmaf(w.x, c4 == 0 ? tk : x[4 * c4 - 1], acc_r);
+              acc_r = fmaf(w.y, x[4 * c4], acc_r);
+              acc_r = fmaf(w.z, x[4 * c4 + 1], acc_r);
+              acc_r = fmaf(w.w, x[4 * c4 + 2], acc_r);
+            }
+            ar[j] = acc_r;
+          }
+        }
         PROF_MARK(1);
         // ---- E6: y1 = relu(D4 + b_u1) -> 8 shared-memory A chunks for the folded up_0 (N = NY)
         mbar_wait(&bars[D4A_FULL], ph);
@@ -379,14 +401,9 @@ __global__ void __launch_bounds__(NT_TC, 1) rollout_tc_kernel(RolloutArgs a, con
         PROF_MARK(15);
         if (h == 0 && live) {
           float gv[KIN], u[KIN];
-          const float tk = __ldg(a.step_tab + 4 * K + k);
 #pragma unroll
-          for (int j = 0; j < KIN; ++j) {  // lanes >= d come out as exact zeros (zero-padded parameters)
-            const float* wr = sm_small + so.r0 + j * KIN;
-            float ar = fmaf(wr[0], tk, sm_small[so.b_r0 + j]);
-#pragma unroll
-            for (int c = 1; c < KIN; ++c) ar = fmaf(wr[c], x[c - 1], ar);
-            gv[j] = fmaxf(au[j] + sm_small[so.bc + j], 0.f) + ar;
+          for (int j = 0; j < KIN; ++j) {
+            gv[j] = fmaxf(au[j] + sm_small[so.bc + j], 0.f) + ar[j];
             eps[j] = stage_f[j * TP + p];
           }
           const float dt = __ldg(a.step_tab + k), sq_ldt = __ldg(a.step_tab + K + k);
