@@ -198,7 +198,7 @@ def gpu_arm(args):
     achieved = k3_flop / (k3_ms * 1e-3) / 1e12
     tensor_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1e_k3_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r1f_k3_traffic.json")
     if os.path.exists(tpath):   # dram bytes of K3a + K3b from the committed ncu capture, per trajectory point
         tj = json.load(open(tpath))
         traffic = tj["dram_bytes_per_point"] * (K_STEPS + 1) * chunk

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-end evidence run (one GPU): tests, smoke, launch list, full ncu captures, bench.  TAG names the outputs.
 set -x
-TAG=${TAG:-r1e}
+TAG=${TAG:-r1f}
 cd "$(dirname "$0")/.."
 timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -3 > gpurun_out/final_pytest_$TAG.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/final_smoke_$TAG.log 2>&1
