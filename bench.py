@@ -284,6 +284,12 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 for multi-process launches: give the CPU reference the host cores it can use
+    # (the same count torch picks by default in a single-process run on this box: the affinity mask, at most 16)
+    try:
+        torch.set_num_threads(max(1, min(16, len(os.sched_getaffinity(0)))))
+    except (AttributeError, OSError):
+        pass
     B = 128
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_baseline(B, 1)
