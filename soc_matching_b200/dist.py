@@ -66,6 +66,10 @@ def sharded_loss_backward(solver, global_batch: int, algorithm: str = "SOCM", gr
     back-propagates; gradients of all parameters and the normalisers are summed with one
     all-reduce.  Returns (global objective, mean(w), std(w)).  The objective of a shard is
     normalised by its own size, so the global value is the shard-size weighted mean."""
+    if algorithm in ("log-variance", "variance", "moment"):
+        raise NotImplementedError(
+            f"{algorithm!r} is a functional of the whole batch (a variance / second moment over all paths), not a mean "
+            "of per-path terms: its shards cannot be combined by summing gradients; run it on one rank")
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     lo, hi = shard_bounds(global_batch, rank, world)
@@ -73,7 +77,8 @@ def sharded_loss_backward(solver, global_batch: int, algorithm: str = "SOCM", gr
     out = solver.loss(hi - lo, algorithm=algorithm, **loss_kw)
     share = (hi - lo) / float(global_batch)
     (out[0] * share).backward()
-    params = [p for p in solver.neural_sde.parameters() if p.grad is not None]
+    # solver.parameters() = the neural SDE's networks and gammas plus the solver's own y0 / gamma (SOCM_exp, main.py:166)
+    params = [p for p in solver.parameters() if p.grad is not None]
     value = (out[0].detach() * share).reshape(1)
     stats = solver.last_stats.clone()
     if world > 1:

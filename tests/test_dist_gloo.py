@@ -27,6 +27,9 @@ class _FakeSolver:
         self.path_offset = 0
         self.last_stats = None
 
+    def parameters(self):
+        return self.neural_sde.parameters()
+
     def loss(self, batch, algorithm="SOCM"):
         idx = torch.arange(self.path_offset, self.path_offset + batch, dtype=torch.float64)
         w = torch.exp(-0.001 * idx)                                    # per-path importance weight
@@ -90,3 +93,11 @@ def test_two_ranks_equal_one_rank():
     assert abs(mean2 - float(mean1)) <= 1e-6 and abs(std2 - float(std1)) <= 1e-6
     assert torch.allclose(ga, ref.neural_sde.a.grad, rtol=1e-5, atol=1e-7)
     assert torch.allclose(gb, ref.neural_sde.b.grad, rtol=1e-5, atol=1e-7)
+
+
+def test_batch_functionals_are_not_sharded():
+    """log-variance / variance / moment couple all paths of the batch: summing shard gradients would be wrong."""
+    import pytest
+    for algo in ("log-variance", "variance", "moment"):
+        with pytest.raises(NotImplementedError):
+            sdist.sharded_loss_backward(_FakeSolver(), 64, algo)
