@@ -97,7 +97,7 @@ def test_two_ranks_equal_one_rank():
 
 def test_batch_functionals_are_not_sharded():
     """log-variance / variance / moment couple all paths of the batch: summing shard gradients would be wrong."""
-    import pytest
+    from soc_matching_b200 import dist as sdist
     for algo in ("log-variance", "variance", "moment"):
         with pytest.raises(NotImplementedError):
             sdist.sharded_loss_backward(_FakeSolver(), 64, algo)
