@@ -79,13 +79,15 @@ __constant__ StageDesc c_stage[N_STAGE_DESC] = {
     {2, {{WG_B, FB_DZ1, 8 * FBB}, {WG_X, FB_XIN, FBB}, {0, 0, 0}, {0, 0, 0}},
      2, {{WG_B, WG_X, 32, 416}, {WG_B + 16384, WG_X, 32, 448}, {0, 0, 0, 0}, {0, 0, 0, 0}}},
     // ---- pass 1: up_1 (both row halves; o2 sits in the A region as the N operand), res_2
-    {3, {{WG_B, FB_DY1, 8 * FBB}, {WG_A, FB_O2, 4 * FBB}, {WG_X, FB_XIN, FBB}, {0, 0, 0}},
-     4, {{WG_B, WG_A, 128, 0}, {WG_B, WG_X, 32, 128}, {WG_B + 16384, WG_A, 128, 160}, {WG_B + 16384, WG_X, 32, 288}}},
-    {3, {{WG_A, FB_DO2, 4 * FBB}, {WG_B, FB_R2, 4 * FBB}, {WG_X, FB_XIN, FBB}, {0, 0, 0}},
-     2, {{WG_A, WG_B, 128, 320}, {WG_A, WG_X, 32, 448}, {0, 0, 0, 0}, {0, 0, 0, 0}}},
+    // (an N operand and the XIN block are placed back to back wherever the sum stays <= 256 rows: one MMA of
+    //  N + 32 columns reads the M operand once instead of twice)
+    {3, {{20480, FB_DY1, 8 * FBB}, {0, FB_O2, 4 * FBB}, {16384, FB_XIN, FBB}, {0, 0, 0}},
+     2, {{20480, 0, 160, 0}, {20480 + 16384, 0, 160, 160}, {0, 0, 0, 0}, {0, 0, 0, 0}}},
+    {3, {{WG_A, FB_DO2, 4 * FBB}, {16384, FB_R2, 4 * FBB}, {32768, FB_XIN, FBB}, {0, 0, 0}},
+     1, {{WG_A, 16384, 160, 320}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}}},
     // ---- pass 2: up_2, down_2 (D[in][out]) + its bias, and the d-sized layers
-    {3, {{WG_A, FB_DY2, 4 * FBB}, {WG_B, FB_R3, 2 * FBB}, {WG_X, FB_XIN, FBB}, {0, 0, 0}},
-     2, {{WG_A, WG_B, 64, 0}, {WG_A, WG_X, 32, 64}, {0, 0, 0, 0}, {0, 0, 0, 0}}},
+    {3, {{WG_A, FB_DY2, 4 * FBB}, {16384, FB_R3, 2 * FBB}, {24576, FB_XIN, FBB}, {0, 0, 0}},
+     1, {{WG_A, 16384, 96, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}}},
     // M is always 128 (an M = 64 accumulator is spread over 16 lanes per TMEM quarter): the d_z3 and d_y0 row
     // blocks are loaded with the neighbouring tensors of the scratch, whose rows the flush ignores
     {4, {{WG_A, FB_R2, 4 * FBB}, {WG_B, FB_DZ3, 4 * FBB}, {WG_B + 16384, FB_DY0, 4 * FBB}, {WG_X, FB_XIN, FBB}},
