@@ -48,9 +48,12 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region.  The sampler is started
+    before the warm-up (nvidia-smi needs a few hundred ms for its first line) and ``stop(t0, t1)`` keeps the samples
+    whose timestamp lies inside the timed region; if that region was too short to contain one, the samples taken
+    under the warm-up load are used instead and the fact is noted."""
 
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
@@ -66,7 +69,15 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self):
+    @staticmethod
+    def _epoch(stamp: str):
+        import datetime
+        try:
+            return datetime.datetime.strptime(stamp.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -75,23 +86,26 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         self.fh.close()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in open(self.path):
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
+                rows.append((self._epoch(parts[0]), float(parts[1]), float(parts[2]),
+                             [n for n, v in zip(names, parts[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
         os.unlink(self.path)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        inside = [r for r in rows if t0 is not None and r[0] is not None and t0 <= r[0] <= t1]
+        used = inside or rows
+        out = {"sm_mhz": statistics.median([r[1] for r in used]) if used else None,
+               "sm_max_mhz": max(r[2] for r in used) if used else None, "samples": len(used),
+               "reasons": sorted({n for r in used for n in r[3]})}
+        if used and not inside:
+            out["note"] = "timed region shorter than the sampling period: samples of the warm-up load"
+        return out
 
 
 def build_problem(dev, batch_local):
@@ -128,20 +142,21 @@ def gpu_arm(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     # ---- device-timed region: exactly K steps, inputs resident in HBM
     solver.kernel_events = {}
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    wall0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(wall0, time.time())
     t_dev = ev0.elapsed_time(ev1) * 1e-3
     kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in solver.kernel_events.items()}
     kernel_n = {k: len(v) for k, v in solver.kernel_events.items()}
