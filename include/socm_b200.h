@@ -143,6 +143,18 @@ int socm_target_gemm_bwd_tc_f32(const float* G, const float* R, int32_t B, int32
 /* SOCM_const_M (method.py:289-369): target_i = sum_{j>=i} a_j + grad_g, i.e. M = I, dM = 0. */
 int socm_target_const_m_f32(const float* R, int32_t B, int32_t K, int32_t d, int32_t ldr,
                             float* target, int32_t ldt, void* stream);
+/* SOCM with stopping times (method.py:484-507, 524-564, 584-690): the per-sample table M(t, s, tau_m) depends on the
+ * path only through its stopping index group[m] = #{k : Phi(x_km) > 0} - 1 (method.py:524-531), so the caller builds
+ * one table per index, transposed: LT[n_groups][(2K+1)d][nrp] (columns of R x target rows, zero left of the block
+ * diagonal), and   target[m][:] = R[m][:] . LT[group[m]].   perm[B] lists the paths sorted by group (the kernels
+ * visit them in that order).  The reference's (K+1, K+1, B, d, d) intermediate never exists. */
+int socm_target_grouped_f32(const float* LT, const float* R, const int32_t* group, const int32_t* perm,
+                            int32_t n_groups, int32_t B, int32_t K, int32_t d, int32_t ldr, int32_t nrp,
+                            float* target, int32_t ldt, void* stream);
+/* dLT[g][c][r] += sum over the paths of group g of R[m][c] G[m][r]  (only the j >= i blocks are written). */
+int socm_target_grouped_bwd_f32(const float* G, const float* R, const int32_t* group, const int32_t* perm,
+                                int32_t n_groups, int32_t B, int32_t K, int32_t d, int32_t ldr, int32_t ldt,
+                                int32_t nrp, float* dLT, void* stream);
 /* SOCM_adjoint (method.py:722-749): target[m][i] = a_i, the adjoint state of path m from the backward recursion
  *   a_K = grad_g(x_K),  a_j = a_{j+1} + dt ((grad_f(x_j) + grad_f(x_{j+1})) / 2 + ((grad_b(x_j) + grad_b(x_{j+1})) / 2) a_{j+1})
  * with the constant dt = T / num_steps of method.py:169.  states: [K+1][B][d].  The loss that follows is the

@@ -140,7 +140,8 @@ def build_case(ref, name):
         x0 = -torch.ones(d)
         kappa = torch.ones(d)
         sigma = torch.eye(d)
-        sde = ref.MolecularDynamics(kappa=kappa, sigma=sigma, use_stopping_time=True, **common)
+        # use_stopping_time selects the M-network class (method.py:117-132): TwoBoundarySigmoidMLP or SigmoidMLP
+        sde = ref.MolecularDynamics(kappa=kappa, sigma=sigma, use_stopping_time=bool(c.get("stopping")), **common)
         tens.update(kappa=kappa)
     else:
         raise ValueError(kind)
@@ -211,14 +212,34 @@ CASES = {
     "c3_ou_quadratic_hard_warm": dict(kind="ou_quadratic", d=3, K=10, B=5, hdims=[24, 16, 8], hdims_M=[12, 12],
                                       lmbd=1.0, gamma=2.0, apq=(1.0, 1.0, 0.5), sf_v=0.1, seed=3,
                                       warm=dict(n_iter=4, lr=2e-4), algorithms=["SOCM", "SOCM_const_M"]),
+    # SOCM_const_M / SOCM_exp / SOCM_adjoint never read use_stopping_time (method.py:289-478, 722-749): plain dts,
+    # no mask, normaliser (K+1) B, although the rollout stops paths (utils.py:33 keys on Phi alone)
     "c4_molecular_dynamics": dict(kind="molecular_dynamics", d=1, K=60, B=32, hdims=[24, 16, 8], hdims_M=[8, 8],
                                   lmbd=1.0, gamma=2.0, seed=8, stopping=True,
-                                  algorithms=["SOCM", "cross_entropy", "log-variance", "moment"]),
+                                  algorithms=["SOCM", "cross_entropy", "log-variance", "moment", "SOCM_const_M",
+                                              "SOCM_adjoint"]),
+    # the same setting run WITHOUT use_stopping_time: SigmoidMLP M(t, s), plain dts in the SOCM target, no mask
+    "c4b_molecular_dynamics_plain": dict(kind="molecular_dynamics", d=1, K=60, B=32, hdims=[24, 16, 8],
+                                         hdims_M=[8, 8], lmbd=1.0, gamma=2.0, seed=8, stopping=False,
+                                         algorithms=["SOCM", "SOCM_const_M", "SOCM_exp", "cross_entropy",
+                                                     "log-variance"]),
     "c5_double_well": dict(kind="double_well", d=4, K=100, B=5, hdims=[24, 16, 8], hdims_M=[12, 12],
                            lmbd=1.0, gamma=6.0, seed=5,
                            algorithms=["SOCM", "SOCM_const_M", "SOCM_exp", "SOCM_adjoint", "cross_entropy", "log-variance", "variance", "moment"]),
     "c5_double_well_fullnet": dict(kind="double_well", d=10, K=100, B=3, hdims=[256, 128, 64], hdims_M=[128, 128],
                                    lmbd=1.0, gamma=6.0, seed=6, param_seed=1234, algorithms=["SOCM", "SOCM_adjoint"]),
+    # BASELINE config 3 at the DEFAULT width: the warm-start table enters the tcgen05 / FFMA-tile kernels (the
+    # reduced-width c3 above only reaches the shape-generic ones).  The reference evaluates its own RestrictedControl
+    # (two jvp's per step); the product and the oracle the tabulated affine form.
+    "c3_full_warm": dict(kind="ou_quadratic", d=20, K=30, B=24, hdims=[256, 128, 64], hdims_M=[128, 128],
+                         lmbd=1.0, gamma=2.0, apq=(1.0, 1.0, 0.5), sf_v=0.1, seed=13, param_seed=2468,
+                         warm=dict(n_iter=4, lr=2e-4), algorithms=["SOCM", "SOCM_const_M"]),
+    # default width at (K+1) B = 65 536 trajectory points = SOCM_LOSS_TC_MIN_POINTS: the default dispatch runs the
+    # tcgen05 K3, so this fixture pins the tensor-core path against the reference's OWN loss and gradients.  The
+    # injected noise is regenerated from `noise_seed` (numpy) and only a subsample of the trajectories is stored.
+    "big_c5_double_well_tc": dict(kind="double_well", d=10, K=63, B=1024, hdims=[256, 128, 64], hdims_M=[128, 128],
+                                  lmbd=1.0, gamma=6.0, seed=16, param_seed=4321, noise_seed=77, keep_paths=48,
+                                  algorithms=["SOCM"]),
 }
 
 
@@ -250,11 +271,34 @@ def run_case(ref, name):
     # ---- rollout (utils.py:17-128) with the reference's own RNG; keep the noise it drew
     torch.manual_seed(1000 + c["seed"])
     state0 = x0.repeat(B, 1)
-    traj = ref.utils.stochastic_trajectories(sde, state0, ts, c["lmbd"])
     names = ["states", "noises", "stop_indicators", "fractional_timesteps", "logw_det", "logw_sto",
              "logw_term", "controls"]
-    for n, v in zip(names, traj):
-        out[f"rollout/{n}"] = v.float().numpy().copy()
+    if c.get("noise_seed") is not None:      # big case: numpy-seeded noise, replayed through torch.randn_like
+        # the noise is selected (NOT the reference's computation on it): paths that keep clear of the ReLU kinks of
+        # the control network, where the gradient is well defined (oracle/socm_oracle.py:kink_free_attempts)
+        root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+        sys.path[:0] = [root, os.path.join(root, "tests")]
+        from oracle import socm_oracle as orc
+        from helpers import seeded_unet          # the same seeded parameters seeded_params() wrote into the reference
+        st = orc.Setting(c["kind"], d, sigma, c["lmbd"], **{k: v for k, v in tens.items() if k not in ("x0", "sigma")})
+        attempts = orc.kink_free_attempts(st, seeded_unet(d, c["hdims"], c["param_seed"], c.get("sf_v", 1.0)), x0, ts,
+                                          c["noise_seed"], B)
+        print(f"  {name}: {int((attempts > 0).sum())} of {B} paths redrawn to stay clear of ReLU kinks")
+        meta["noise_seed"], meta["keep_paths"] = c["noise_seed"], c["keep_paths"]
+        out["noise_attempts"] = attempts.astype(np.int16)
+        fixed = orc.path_noise(c["noise_seed"], attempts, K, d)
+        with _ReplayNoise(fixed):
+            traj = ref.utils.stochastic_trajectories(sde, state0, ts, c["lmbd"])
+        kp = c["keep_paths"]
+        for n, v in zip(names, traj):
+            v = v.float()
+            if n == "noises":
+                continue
+            out[f"rollout_sub/{n}"] = (v[:, :kp] if v.dim() >= 2 else v).numpy().copy()
+    else:
+        traj = ref.utils.stochastic_trajectories(sde, state0, ts, c["lmbd"])
+        for n, v in zip(names, traj):
+            out[f"rollout/{n}"] = v.float().numpy().copy()
     noises = traj[1]
     if c.get("stopping"):
         n_stopped = int((traj[2][-1] == 0).sum())

@@ -529,6 +529,66 @@ def socm_loss(
 
 
 # --------------------------------------------------------------------------------------
+# Kink-free test inputs
+# --------------------------------------------------------------------------------------
+def unet_preactivations64(unet: Dict[str, Tensor], tx: Tensor):
+    """The six pre-ReLU tensors of FullyConnectedUNet.forward (models.py:233-242) in fp64."""
+    P = {k: v.double() for k, v in unet.items()}
+
+    def lin(name: str, v: Tensor) -> Tensor:
+        return F.linear(v, P[name + ".0.weight"], P[name + ".0.bias"])
+
+    z1 = lin("down_0", tx)
+    r1 = torch.relu(z1)
+    z2 = lin("down_1", r1)
+    r2 = torch.relu(z2)
+    z3 = lin("down_2", r2)
+    r3 = torch.relu(z3)
+    y2 = lin("up_2", r3)
+    o2 = torch.relu(y2) + lin("res_2", r2)
+    y1 = lin("up_1", o2)
+    o1 = torch.relu(y1) + lin("res_1", r1)
+    return [z1, z2, z3, y2, y1, lin("up_0", o1)]
+
+
+def path_noise(seed: int, attempts, K: int, d: int) -> Tensor:
+    """(K, B, d) standard normal increments, path m drawn from numpy's default_rng([seed, m, attempts[m]]): a fixture
+    stores ``seed`` and the small integer array ``attempts`` instead of the noise itself."""
+    import numpy as np
+
+    cols = [np.random.default_rng([int(seed), m, int(a)]).standard_normal((K, d)).astype(np.float32)
+            for m, a in enumerate(attempts)]
+    return torch.from_numpy(np.stack(cols, axis=1))
+
+
+def kink_free_attempts(st: Setting, unet: Dict[str, Tensor], x0: Tensor, ts: Tensor, seed: int, B: int,
+                       warm: Optional[WarmStartTable] = None, rel_delta: float = 4e-6, max_rounds: int = 400):
+    """Redraw the Brownian increments of every path that comes within ``rel_delta * rms(layer)`` of a ReLU kink of
+    the control network at any of its K+1 points (fp64 evaluation along the oracle's rollout) until none does.
+
+    d loss / d theta is discontinuous where a pre-activation crosses zero: the mask of that unit is decided by the
+    last bits of a 64..256-term sum, so any two fp32 evaluations of the same network (MKL vs cuBLAS, FFMA vs tensor
+    cores) may pick different masks there, and ONE flipped unit moves a gradient tensor of a few-thousand-point batch
+    by ~1e-3 although both results are valid sub-gradients.  On paths that keep a safe distance from every kink the
+    comparison measures arithmetic.  Returns the integer array ``attempts`` for :func:`path_noise`."""
+    import numpy as np
+
+    K, d = ts.shape[0] - 1, st.d
+    attempts = np.zeros(B, dtype=np.int64)
+    for _ in range(max_rounds):
+        noises = path_noise(seed, attempts, K, d)
+        states = rollout(st, unet, x0.repeat(B, 1), ts, noises=noises, warm=warm)[0]
+        tx = torch.cat([ts.reshape(-1, 1, 1).expand(K + 1, B, 1), states], -1).double()
+        near = torch.zeros(B, dtype=torch.bool)
+        for z in unet_preactivations64(unet, tx):
+            near |= (z.abs() < rel_delta * z.pow(2).mean().sqrt()).any(-1).any(0)
+        if not bool(near.any()):
+            return attempts
+        attempts[near.numpy()] += 1
+    raise RuntimeError("kink_free_attempts: no kink-free draw found")
+
+
+# --------------------------------------------------------------------------------------
 # Philox4x32-10 (counter-based RNG used by the CUDA rollout when noise is not injected)
 # --------------------------------------------------------------------------------------
 def philox4x32_10(counter, key):

@@ -63,6 +63,8 @@ PROTOTYPES = {
     "socm_target_gemm_bwd_tc_workspace_bytes": (_i64, [_i32, _i32, _i32]),
     "socm_target_gemm_bwd_tc_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp]),
     "socm_target_const_m_f32": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "socm_target_grouped_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "socm_target_grouped_bwd_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "socm_target_adjoint_f32": (C.c_int, [C.POINTER(Setting), _vp, _i32, _i32, _f32, _vp, _i32, _vp]),
     "socm_adam_step_f32": (C.c_int, [C.POINTER(AdamTensor), _i32, C.c_double, C.c_double, C.c_double, _i32, _i32, _vp]),
     "socm_loss_workspace_bytes": (_i64, [C.POINTER(UNet), _i32, _i32]),

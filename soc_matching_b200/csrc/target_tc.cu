@@ -238,6 +238,8 @@ using namespace socm;
 
 extern "C" int64_t socm_target_gemm_tc_workspace_bytes(int32_t K, int32_t d) {
   if (K < 1 || d < 1) return -1;
+  // same bound as socm_target_gemm_tc_f32: make_plan fills fixed-size tables (K2_MAX_BLOCKS row blocks)
+  if (((K + 1) * d + tc::K2_NB - 1) / tc::K2_NB > tc::K2_MAX_BLOCKS) return -1;
   const tc::K2Plan p = tc::make_plan((K + 1) * d, (2 * K + 1) * d, d);
   return (int64_t)p.slot_begin[p.n_blocks] * tc::MAIN_BYTES + 1024;
 }

@@ -64,25 +64,43 @@ def merge_weight_stats(stats: torch.Tensor, n_paths: int):
 def sharded_loss_backward(solver, global_batch: int, algorithm: str = "SOCM", group=None, **loss_kw):
     """One data-parallel SOCM iteration: every rank runs ``solver.loss`` on its shard and
     back-propagates; gradients of all parameters and the normalisers are summed with one
-    all-reduce.  Returns (global objective, mean(w), std(w)).  The objective of a shard is
-    normalised by its own size, so the global value is the shard-size weighted mean."""
+    all-reduce.  Returns (global objective, mean(w), std(w)).
+
+    Without stopping times the objective of a shard is normalised by its own size (K+1) n_shard, so the
+    global value is the shard-size weighted mean.  With ``use_stopping_time`` (SOCM only, method.py:711-715)
+    the reference divides by the sum of ALL stop indicators: each shard is normalised by its own sum z_r, so
+    the ranks first all-reduce z (one fp64 scalar) and weight their shard by z_r / z before back-propagating --
+    the result does not depend on the world size."""
     if algorithm in ("log-variance", "variance", "moment"):
         raise NotImplementedError(
             f"{algorithm!r} is a functional of the whole batch (a variance / second moment over all paths), not a mean "
             "of per-path terms: its shards cannot be combined by summing gradients; run it on one rank")
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world > global_batch:
+        raise ValueError(f"world size {world} exceeds the global batch {global_batch}: a rank would own no path")
     lo, hi = shard_bounds(global_batch, rank, world)
     solver.path_offset = lo
     out = solver.loss(hi - lo, algorithm=algorithm, **loss_kw)
-    share = (hi - lo) / float(global_batch)
-    (out[0] * share).backward()
-    # solver.parameters() = the neural SDE's networks and gammas plus the solver's own y0 / gamma (SOCM_exp, main.py:166)
-    params = [p for p in solver.parameters() if p.grad is not None]
-    value = (out[0].detach() * share).reshape(1)
     stats = solver.last_stats.clone()
+    share = (hi - lo) / float(global_batch)
+    if loss_kw.get("use_stopping_time") and algorithm == "SOCM":
+        z_all = stats[2:3].clone()
+        if world > 1:
+            dist.all_reduce(z_all, group=group)
+        share = float(stats[2] / z_all[0])
+    (out[0] * share).backward()
+    # Deterministic reduction list: every parameter of the solver (the neural SDE's networks and gammas plus the
+    # solver's own y0 / gamma of SOCM_exp, main.py:166), in registration order, with a zero standing in for a
+    # gradient this rank did not produce -- all ranks then send flat buffers of the same length.
+    params = list(solver.parameters())
+    grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
+    value = (out[0].detach() * share).reshape(1)
     if world > 1:
-        allreduce_flat([p.grad for p in params] + [value], group)
+        allreduce_flat(grads + [value], group)
         dist.all_reduce(stats, group=group)  # fp64 sums stay fp64
+        for p, g in zip(params, grads):
+            if p.grad is None and bool(torch.any(g != 0)):
+                p.grad = g
     mean_w, std_w = merge_weight_stats(stats, global_batch)
     return value[0], mean_w, std_w

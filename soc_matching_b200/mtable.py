@@ -92,13 +92,16 @@ def build_L(m_all: torch.Tensor, dm_all: torch.Tensor, grid: PairGrid, ldr: int)
     return L.contiguous()
 
 
-def dense_tables(m_all: torch.Tensor, dm_all: torch.Tensor, K: int):
-    """Per-sample variant (stopping times): (P, B, d, d) -> two (K+1, K+1, B, d, d) tables, zero
-    for j < i (method.py:502-507, 556-564)."""
-    P, B, d, _ = m_all.shape
-    iu = torch.triu_indices(K + 1, K + 1, device=m_all.device)
-    M = torch.zeros(K + 1, K + 1, B, d, d, device=m_all.device, dtype=m_all.dtype)
-    dM = torch.zeros_like(M)
-    M = M.index_put((iu[0], iu[1]), m_all)
-    dM = dM.index_put((iu[0], iu[1]), dm_all)
-    return M, dM
+def build_LT_grouped(m_all: torch.Tensor, dm_all: torch.Tensor, grid: PairGrid, nrp: int) -> torch.Tensor:
+    """Stopping-time variant: (P, Q, d, d) x2 (one table per stopping index q, method.py:524-564) ->
+    LT (Q, (2K+1)d, nrp) fp32, the transposed block table of csrc/target_grouped.cu:
+        LT[q][(j', l)][(i, k)] = block (i, j') of [M_i0 dM_i0 ... M_iK] for index q, entry (k, l),
+    zero left of the block diagonal and in the row padding."""
+    K, d, Q = grid.K, m_all.shape[-1], m_all.shape[1]
+    zero = torch.zeros(1, Q, d, d, device=m_all.device, dtype=m_all.dtype)
+    src = torch.cat([m_all, dm_all, zero], dim=0)                                  # (2P+1, Q, d, d)
+    blocks = _GatherBlocks.apply(src, grid.block_index, grid.inverse_index)        # (K+1, 2K+1, Q, d(k), d(l))
+    LT = blocks.permute(2, 1, 4, 0, 3).reshape(Q, (2 * K + 1) * d, (K + 1) * d)
+    if nrp > LT.shape[2]:
+        LT = torch.nn.functional.pad(LT, (0, nrp - LT.shape[2]))
+    return LT.contiguous()

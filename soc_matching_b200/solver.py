@@ -141,12 +141,8 @@ class SOC_Solver(nn.Module):
             raise NotImplementedError(
                 f"algorithm {algorithm!r}: SOCM, SOCM_const_M, SOCM_exp, SOCM_adjoint and {PATH_FUNCTIONAL_LOSSES} run on "
                 "the B200 path; rel_entropy (back-propagation through the rollout) does not (SURVEY.md section 8f)")
-        if algorithm == "SOCM_exp" and use_stopping_time:
-            raise NotImplementedError("SOCM_exp ignores stopping times in the reference (method.py:371-478)")
         if compute_L2_error and optimal_control is None:
             raise ValueError("compute_L2_error=True needs optimal_control (a callable (ts, states, t_is_tensor=True))")
-        if algorithm == "SOCM_adjoint" and use_stopping_time:
-            raise NotImplementedError("SOCM_adjoint with stopping times is not defined by the reference (method.py:722-749)")
         lib = _lib.load()
         sde = self.neural_sde
         dev = self.x0.device
@@ -155,9 +151,14 @@ class SOC_Solver(nn.Module):
         desc.c_struct.lmbd = float(self.lmbd)
         d, K, B = desc.d, self.num_steps, int(batch_size)
         ts = self.ts.to(dev)
-        stopping = bool(use_stopping_time)
+        # Only the SOCM branch of the reference looks at use_stopping_time (method.py:484-720): SOCM_const_M
+        # (289-369), SOCM_exp (371-478) and SOCM_adjoint (722-749) never read the flag -- no mask, plain dts,
+        # normaliser (K+1) B -- even when the rollout itself stopped paths (utils.py:33 keys on Phi alone).
+        stopping = bool(use_stopping_time) and algorithm == "SOCM"
         if stopping and not desc.has_stopping:
             raise _lib.SocmError("use_stopping_time=True needs a setting with a stopping function Phi")
+        if B <= 0:
+            raise ValueError(f"batch_size must be positive, got {B}")
         # warm start: the reference only applies it in the loss if u_warm_start is passed AND
         # use_warm_start (method.py:280); the rollout uses the sde's own flags (method.py:77).
         warm_loss = None
@@ -196,6 +197,22 @@ class SOC_Solver(nn.Module):
             eye = torch.eye(d, **f32)
             L = mtable.build_L(decay * eye, (-gamma_p.to(dev)).reshape(1, 1, 1) * decay * eye, grid, ldr)
             dL = torch.zeros(nrows, ldr, **f32)
+        LT = dLT = None
+        if stopping:
+            # method.py:484-507, 524-564: M(t, s, tau_m) depends on the path only through its stopping index
+            # q_m = #{k : Phi(x_km) > 0} - 1 (tau_m = q_m / K), so there are K+1 tables, built once per iteration
+            # from the M-network (B-independent, differentiable) -- csrc/target_grouped.cu contracts them per path
+            n_groups = K + 1
+            table_bytes = 4 * n_groups * (2 * K + 1) * d * ldt
+            if table_bytes > (8 << 30):
+                raise NotImplementedError(
+                    f"stopping-time SOCM keeps one (2K+1)d x (K+1)d table per stopping index: {table_bytes / 2**30:.1f} "
+                    "GiB at this (K, d); the reference's setting is d = 1 (molecular_dynamics.py)")
+            grid = self._grid()
+            tau_vals = torch.arange(n_groups, **f32) / K                          # (cnt - 1) / K, method.py:524-530
+            m_all, dm_all = sde.M.value_and_ds(grid.t, grid.s, tau_vals.unsqueeze(0).expand(grid.P, n_groups))
+            LT = mtable.build_LT_grouped(m_all, dm_all, grid, ldt)
+            dLT = torch.zeros_like(LT)
 
         if self.chunk_paths is None:
             # whole waves of persistent CTAs (one 128-path tile per SM and wave): no ragged last wave
@@ -215,14 +232,17 @@ class SOC_Solver(nn.Module):
         seed = simulate.next_seed()
         scale = 1.0 if stopping else 1.0 / ((K + 1) * B)                    # method.py:715 / 720
         warm_struct = simulate._warm_struct(warm_loss.A_loss, warm_loss.c_loss) if warm_loss is not None else None
-        target_graph = None   # stopping case: the torch-side target (keeps the autograd graph)
         k2_ws = None          # workspace of the tcgen05 target GEMM
+        simt_target = self.force_ffma or self.force_generic or self.force_simt_target
         k2b_ws, k2b_nb = None, -1
-        if stopping and B > chunk:
-            raise NotImplementedError("stopping-time SOCM is not chunked yet: batch_size must be <= chunk_paths")
 
         x0_rep = self.x0.detach().float().reshape(1, d)
         ts_f32 = ts.float().contiguous()
+        # method.py:648-673: the fractional time steps of the rollout enter the target only under use_stopping_time;
+        # otherwise the plain dts do (they coincide unless the setting has a stopping function)
+        plain_dt = None
+        if desc.has_stopping and not stopping:
+            plain_dt = (ts_f32[1:] - ts_f32[:-1]).reshape(K, 1).expand(K, chunk).contiguous()
         self.launch_count = 0
         l2_sum = torch.zeros((), device=dev, dtype=torch.float64) if compute_L2_error else None
         for start in range(0, B, chunk):
@@ -239,7 +259,8 @@ class SOC_Solver(nn.Module):
                              force_generic=self.force_generic, force_ffma=self.force_ffma, timer=self._timed)
             self._timed("prep", 2, lib.socm_target_prep_f32,
                         desc.c_struct, _lib.ptr(wsp.states), _lib.ptr(wsp.noises), _lib.ptr(wsp.controls),
-                        _lib.ptr(wsp.eff_dt), wsp.lw[0].data_ptr(), wsp.lw[1].data_ptr(), wsp.lw[2].data_ptr(), nb, K,
+                        _lib.ptr(wsp.eff_dt if plain_dt is None else plain_dt[:, :nb].contiguous()),
+                        wsp.lw[0].data_ptr(), wsp.lw[1].data_ptr(), wsp.lw[2].data_ptr(), nb, K,
                         _lib.ptr(R), ldr, _lib.ptr(wbuf), stream)
             self._timed("stats", 1, lib.socm_weight_stats_f32, _lib.ptr(wbuf),
                         _lib.ptr(wsp.stop) if stopping else None, nb, K, _lib.ptr(stats), stream)
@@ -250,18 +271,24 @@ class SOC_Solver(nn.Module):
                 self._timed("target", 1, lib.socm_target_adjoint_f32, desc.c_struct, _lib.ptr(wsp.states), nb, K,
                             float(self.dt), _lib.ptr(target), ldt, stream)
             elif not stopping:
-                if self.force_ffma or self.force_generic or self.force_simt_target:      # fp32 SIMT GEMM
+                if k2_ws is None and not simt_target:
+                    nbytes = int(lib.socm_target_gemm_tc_workspace_bytes(K, d))
+                    if nbytes < 0:        # (K+1) d beyond the tcgen05 kernel's plan tables: fp32 SIMT GEMMs instead
+                        simt_target = True
+                    else:
+                        k2_ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+                if simt_target:                                # fp32 SIMT GEMM
                     self._timed("target", 1, lib.socm_target_gemm_f32, _lib.ptr(L.detach()), _lib.ptr(R), nb, K, d,
                                 ldr, _lib.ptr(target), ldt, stream)
                 else:                                          # tcgen05, 3xTF32 (tape pack + GEMM)
-                    if k2_ws is None:
-                        k2_ws = torch.empty(int(lib.socm_target_gemm_tc_workspace_bytes(K, d)), device=dev,
-                                            dtype=torch.uint8)
                     self._timed("target", 2, lib.socm_target_gemm_tc_f32, _lib.ptr(L.detach()), _lib.ptr(R), nb, K, d,
                                 ldr, _lib.ptr(target), ldt, k2_ws.data_ptr(), stream)
             else:
-                target_graph = self._stopping_target(sde, wsp, R, ts, K, d, nb)
-                target[:, :nrows].copy_(target_graph.detach())
+                # stopping index of every path (Phi(x) = -x_0 > 0, method.py:524-530) and the order that groups them
+                q_idx = ((wsp.states[..., 0] < 0).sum(dim=0) - 1).to(torch.int32).contiguous()
+                perm = torch.sort(q_idx, stable=True)[1].to(torch.int32).contiguous()
+                self._timed("target", 1, lib.socm_target_grouped_f32, _lib.ptr(LT.detach()), _lib.ptr(R),
+                            q_idx.data_ptr(), perm.data_ptr(), K + 1, nb, K, d, ldr, ldt, _lib.ptr(target), ldt, stream)
             self._timed("loss_fwdbwd", self._k3_launches(udesc, nb, K), lib.socm_unet_loss_fwdbwd_f32,
                         desc.c_struct, udesc, warm_struct, _lib.ptr(ts_f32), _lib.ptr(wsp.states),
                         _lib.ptr(target), ldt, _lib.ptr(wbuf), _lib.ptr(wsp.stop) if stopping else None, scale, nb, K,
@@ -270,7 +297,7 @@ class SOC_Solver(nn.Module):
                         | (_lib.LOSS_FORCE_FFMA if self.force_ffma else 0)
                         | (_lib.LOSS_FORCE_TC if self.force_tc else 0), stream)
             if L is not None:
-                if self.force_ffma or self.force_generic or self.force_simt_target:      # fp32 SIMT GEMM
+                if simt_target:                                # fp32 SIMT GEMM
                     self._timed("target_bwd", 1, lib.socm_target_gemm_bwd_f32, _lib.ptr(G), _lib.ptr(R), nb, K, d, ldr,
                                 ldt, _lib.ptr(dL), 1, stream)
                 else:                                          # tcgen05, 3xTF32 (2 transposes + GEMM)
@@ -280,6 +307,9 @@ class SOC_Solver(nn.Module):
                         k2b_nb = nb
                     self._timed("target_bwd", 3, lib.socm_target_gemm_bwd_tc_f32, _lib.ptr(G), _lib.ptr(R), nb, K, d,
                                 ldr, ldt, _lib.ptr(dL), 1, k2b_ws.data_ptr(), stream)
+            if stopping:
+                self._timed("target_bwd", 1, lib.socm_target_grouped_bwd_f32, _lib.ptr(G), _lib.ptr(R), q_idx.data_ptr(),
+                            perm.data_ptr(), K + 1, nb, K, d, ldr, ldt, ldt, _lib.ptr(dLT), stream)
             if compute_L2_error:
                 l2_sum += self._l2_error_sum(sde, unet, optimal_control, warm_loss, ts_f32, wsp.states, wbuf)
             if getattr(self, "_debug_keep", False):   # scripts/k3_truth.py: inputs of the last K3 call
@@ -294,7 +324,7 @@ class SOC_Solver(nn.Module):
             z = stats[2]                                                   # sum(stop_indicators), method.py:715
             value = value / z
             grad_flat = (grad_flat.double() / z).float()
-            lead, lead_grad = target_graph, (G[:, :nrows].double() / z).float()
+            lead, lead_grad = LT, (dLT.double() / z).float()
         objective = _FusedObjective.apply(value.float(), lead, lead_grad, grad_flat, *uparams)
 
         self.last_stats = stats
@@ -329,6 +359,16 @@ class SOC_Solver(nn.Module):
         d, K, B = desc.d, self.num_steps, int(batch_size)
         if stopping and not desc.has_stopping:
             raise _lib.SocmError("use_stopping_time=True needs a setting with a stopping function Phi")
+        if B <= 0:
+            raise ValueError(f"batch_size must be positive, got {B}")
+        # Memory bound: these objectives are functionals of ALL per-path sums S_m (a variance / second moment over
+        # the batch), so the value side keeps about ten (K+1) x B x d fp32 tensors alive at once; unlike the SOCM
+        # path it is not chunked.  Refuse batches beyond one chunk instead of running the box out of memory.
+        limit = int(self.chunk_paths) if self.chunk_paths else 4 * 128 * 148
+        if B > limit:
+            raise NotImplementedError(
+                f"{algorithm!r} keeps ~10 (K+1) x B x d tensors resident and is not chunked: batch_size {B} exceeds "
+                f"chunk_paths = {limit}")
         ts = self.ts.to(dev).float().contiguous()
         lam = float(self.lmbd)
         unet = sde.nabla_V
@@ -424,24 +464,6 @@ class SOC_Solver(nn.Module):
         with torch.no_grad():
             target_control = optimal_control(ts, states, t_is_tensor=True).detach()
         return torch.sum(((target_control - learned) ** 2).double() * w.double().reshape(1, -1, 1))
-
-    # ------------------------------------------------------------------ stopping-time target (torch side)
-    def _stopping_target(self, sde, wsp, R, ts, K, d, nb):
-        """Per-sample M(t, s, tau) (method.py:484-507, 524-564, 584-690): the table depends on the
-        path through its stopping index, so the contraction is a batched (per path) triangular
-        mat-vec, done with torch ops on the GPU (d = 1 in the reference's setting)."""
-        grid = self._grid()
-        alive_cnt = (wsp.states[..., 0] < 0).to(torch.int32).sum(dim=0)     # Phi(x) = -x_0 > 0
-        tau = (alive_cnt - 1).to(torch.float32) / K                         # method.py:524-530
-        tau_vec = tau.unsqueeze(0).expand(grid.P, nb)
-        m_all, dm_all = sde.M.value_and_ds(grid.t, grid.s, tau_vec)
-        M, dM = mtable.dense_tables(m_all, dm_all, K)
-        Rv = R[:, : (2 * K + 1) * d]
-        ac = Rv[:, : 2 * K * d].reshape(nb, K, 2, d)
-        a, c, gg = ac[:, :, 0], ac[:, :, 1], Rv[:, 2 * K * d:]
-        tgt = (torch.einsum("ijmkl,mjl->mik", M[:, :-1], a) + torch.einsum("ijmkl,mjl->mik", dM[:, :-1], c)
-               + torch.einsum("imkl,ml->mik", M[:, -1], gg))
-        return tgt.reshape(nb, (K + 1) * d)
 
 
 class _WarmView:

@@ -19,8 +19,10 @@ from oracle import socm_oracle as orc  # noqa: E402  (tests are allowed to use t
 UNET_LAYERS = ["down_0", "down_1", "down_2", "res_0", "res_1", "res_2", "up_2", "up_1", "up_0"]
 
 
-def golden_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+def golden_names(big=False):
+    """Fixture names; the ``big_*`` fixtures (subsampled trajectories, seeded noise) are listed separately."""
+    names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return [n for n in names if n.startswith("big_") == big]
 
 
 def rel_l2(a, b) -> float:
@@ -105,7 +107,17 @@ class Golden:
             self.warm = orc.WarmStartTable(t("warm/A_roll"), t("warm/c_roll"), t("warm/A_loss"), t("warm/c_loss"))
         self.rollout_names = ["states", "noises", "stop_indicators", "fractional_timesteps",
                               "logw_det", "logw_sto", "logw_term", "controls"]
-        self.traj = tuple(t(f"rollout/{n}") for n in self.rollout_names)
+        self.big = m.get("noise_seed") is not None
+        if self.big:
+            # full noise regenerated from the seed (+ per-path redraw counts, kink-free selection); the reference's
+            # trajectories are stored for the first
+            # `keep_paths` paths only (log-weights for all paths): self.traj_sub, self.noises
+            self.noises = orc.path_noise(m["noise_seed"], z["noise_attempts"], m["K"], m["d"])
+            self.traj_sub = {n: t(f"rollout_sub/{n}") for n in self.rollout_names if n != "noises"}
+            self.traj = None
+        else:
+            self.traj = tuple(t(f"rollout/{n}") for n in self.rollout_names)
+            self.noises = self.traj[1]
 
     def grads(self, algo):
         pre = f"{algo}/grad/"

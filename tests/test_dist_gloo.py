@@ -30,13 +30,15 @@ class _FakeSolver:
     def parameters(self):
         return self.neural_sde.parameters()
 
-    def loss(self, batch, algorithm="SOCM"):
+    def loss(self, batch, algorithm="SOCM", use_stopping_time=False):
         idx = torch.arange(self.path_offset, self.path_offset + batch, dtype=torch.float64)
         w = torch.exp(-0.001 * idx)                                    # per-path importance weight
         feat = torch.stack([torch.sin(idx * (k + 1) * 0.01) for k in range(7)], 1).float()
         per_path = (feat @ self.neural_sde.a) ** 2 + (self.neural_sde.b.sum() * torch.cos(idx * 0.02).float()) ** 2
-        obj = (per_path * w.float()).sum() / batch                     # shard-normalised, like method.py:720
-        self.last_stats = torch.stack([w.sum(), (w * w).sum(), torch.tensor(float(batch), dtype=torch.float64)])
+        alive = 1.0 + (idx % 5)                                        # "sum of stop indicators" of each path
+        z = alive.sum() if use_stopping_time else torch.tensor(float(batch), dtype=torch.float64)
+        obj = (per_path * w.float()).sum() / z.float()                 # shard-normalised, like method.py:715 / 720
+        self.last_stats = torch.stack([w.sum(), (w * w).sum(), z])
         return (obj, None, None, None, None, None, None, None)
 
 
@@ -48,14 +50,15 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, batch, out):
+def _worker(rank, world, port, batch, out, stopping=False):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
                       MASTER_PORT=str(port))
     from soc_matching_b200 import dist as sdist
     r, w, _ = sdist.init_from_env("gloo")
     assert (r, w) == (rank, world)
     solver = _FakeSolver()
-    val, mean_w, std_w = sdist.sharded_loss_backward(solver, batch, "SOCM")
+    kw = {"use_stopping_time": True} if stopping else {}
+    val, mean_w, std_w = sdist.sharded_loss_backward(solver, batch, "SOCM", **kw)
     if rank == 0:
         out.put((float(val), float(mean_w), float(std_w), solver.neural_sde.a.grad.clone(), solver.neural_sde.b.grad.clone()))
     torch.distributed.barrier()
@@ -74,15 +77,19 @@ def test_shard_bounds_cover_the_batch():
 
 
 @pytest.mark.timeout(180)
-def test_two_ranks_equal_one_rank():
+@pytest.mark.parametrize("stopping", [False, True])
+def test_two_ranks_equal_one_rank(stopping):
+    """stopping=True: the objective is normalised by the GLOBAL sum of stop indicators (method.py:715), so the shards
+    are weighted by z_shard / z_total, not by their path counts."""
     batch = 1001                                                        # ragged: 501 + 500 paths
     from soc_matching_b200 import dist as sdist
     ref = _FakeSolver()
-    val1, mean1, std1 = sdist.sharded_loss_backward(ref, batch, "SOCM")  # no process group: world = 1
+    kw = {"use_stopping_time": True} if stopping else {}
+    val1, mean1, std1 = sdist.sharded_loss_backward(ref, batch, "SOCM", **kw)  # no process group: world = 1
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, batch, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, batch, out, stopping)) for r in range(2)]
     for p in procs:
         p.start()
     val2, mean2, std2, ga, gb = out.get(timeout=120)
@@ -101,3 +108,10 @@ def test_batch_functionals_are_not_sharded():
     for algo in ("log-variance", "variance", "moment"):
         with pytest.raises(NotImplementedError):
             sdist.sharded_loss_backward(_FakeSolver(), 64, algo)
+
+
+def test_more_ranks_than_paths_is_rejected():
+    from soc_matching_b200 import dist as sdist
+    solver = _FakeSolver()
+    sdist.sharded_loss_backward(solver, 1, "SOCM")      # world = 1: fine
+    assert all(p.grad is not None for p in solver.parameters())
