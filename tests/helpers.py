@@ -3,6 +3,7 @@ from __future__ import annotations
 
 import glob
 import json
+import math
 import os
 import sys
 
@@ -172,3 +173,42 @@ def random_setting(kind: str, d: int, seed: int, lmbd: float = 1.0, dense_sigma:
     if kind == "double_well":
         return orc.Setting(kind, d, sigma, lmbd, kappa=kappa, nu=nu)
     return orc.Setting(kind, d, eye.clone(), lmbd, kappa=torch.ones(d))
+
+
+def gpu_kink_free_noise(sde, x0, ts, B, seed, rel_delta=4e-6, max_rounds=60, slab=16):
+    """GPU twin of ``orc.kink_free_attempts`` for batches the CPU oracle cannot roll out (a full bench chunk): injected
+    noise (K, B, d) on the device such that no path comes within ``rel_delta * rms(layer)`` of a ReLU kink of the control
+    network -- rollout by the product's exact-fp32 FFMA kernel, pre-activations by torch fp64 on the GPU in slabs of
+    grid times.  See the oracle function for why gradient parity is only well defined on such paths."""
+    import soc_matching_b200 as sb  # noqa: F401
+    from soc_matching_b200 import simulate
+    dev = x0.device
+    K, d = ts.shape[0] - 1, sde.dim
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    noises = torch.randn(K, B, d, device=dev, generator=gen)
+    unet = {k: v.detach() for k, v in sde.nabla_V.state_dict().items()}
+    x0b = x0.reshape(1, d).expand(B, d).contiguous()
+    rms = None
+    for _ in range(max_rounds):
+        states = simulate.rollout(sde, x0b, ts, sde.lmbd, noises=noises, force_ffma=True).states
+        near = torch.zeros(B, dtype=torch.bool, device=dev)
+        sums = [0.0] * 6
+        for i0 in range(0, K + 1, slab):
+            i1 = min(K + 1, i0 + slab)
+            tx = torch.cat([ts[i0:i1].reshape(-1, 1, 1).expand(i1 - i0, B, 1), states[i0:i1]], -1).double()
+            pre = orc.unet_preactivations64(unet, tx)
+            if rms is None:
+                for j, z in enumerate(pre):
+                    sums[j] += float(z.pow(2).sum())
+            else:
+                for j, z in enumerate(pre):
+                    near |= (z.abs() < rel_delta * rms[j]).any(-1).any(0)
+        if rms is None:   # first pass only measures the layer scales (they barely move when a few paths are redrawn)
+            widths = [256, 128, 64, 128, 256, d]
+            rms = [math.sqrt(s / ((K + 1) * B * w)) for s, w in zip(sums, widths)]
+            continue
+        n = int(near.sum())
+        if n == 0:
+            return noises
+        noises[:, near] = torch.randn(K, n, d, device=dev, generator=gen)
+    raise AssertionError("gpu_kink_free_noise: no kink-free draw found")

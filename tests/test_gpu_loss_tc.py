@@ -1,15 +1,16 @@
 """tcgen05 K3 (csrc/loss_tc.cu + csrc/wgrad_tc.cu), called through the C ABI with SOCM_LOSS_FORCE_TC.
 
-The forward pass is 3xTF32 (2e-6 from fp32), so a pre-activation that is within ~1e-6 of zero can get
-the other ReLU mask than in the reference -- about one unit in 5e5 -- and that unit's whole gradient
-contribution flips.  The arithmetic check below therefore uses points that are provably away from
-every kink (|pre-activation| > 1e-4 in an fp64 evaluation), where loss and gradients must agree with
-torch fp64 autograd to 2e-5 / 1e-4 (north star: 1e-4); a second test runs the public API end to end."""
+The forward pass is 3xTF32 (4e-7 from fp32 per network evaluation), so a pre-activation that is within ~1e-6 of zero
+can get the other ReLU mask than in an fp32 evaluation -- and that unit's whole gradient contribution flips (one flip
+moves a gradient tensor of a few-thousand-point batch by ~1e-3; the same happens between any two fp32 evaluations,
+only 4x less often).  Every comparison below therefore runs on KINK-FREE inputs: points / paths that keep a safe
+distance from every kink (oracle/socm_oracle.py:kink_free_attempts, tests/helpers.py:gpu_kink_free_noise), where the
+gradient is well defined and the north star's tolerances -- loss 1e-5..1e-4, every gradient tensor 1e-4 -- hold."""
 import pytest
 import torch
 import torch.nn.functional as F
 
-from helpers import make_product_sde, orc, random_setting, rel_l2, seeded_mnet, seeded_unet
+from helpers import gpu_kink_free_noise, make_product_sde, orc, random_setting, rel_l2, seeded_mnet, seeded_unet
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -117,16 +118,16 @@ def test_socm_iteration_with_tc_k3_matches_oracle(kind, d, K, B):
 
 
 def test_tc_k3_is_the_default_for_large_batches_and_agrees_with_ffma():
-    """(K+1)*B >= SOCM_LOSS_TC_MIN_POINTS dispatches to the tcgen05 kernels: loss 1e-5, G 1e-5 and
-    gradients 2e-3 against the fp32 FFMA kernel on the same rollout (the gradient bound allows for the
-    ReLU-mask flips explained in the module docstring; without flips the two agree to 5e-6)."""
+    """(K+1)*B >= SOCM_LOSS_TC_MIN_POINTS dispatches to the tcgen05 kernels: loss 1e-5 and every gradient tensor
+    1e-4 against the fp32 FFMA kernel on the same kink-free rollout."""
     import soc_matching_b200 as sb
     d, K, B = 10, 63, 1024
     st = random_setting("double_well", d, seed=4)
     hd, hm = [256, 128, 64], [128, 128]
     unet, mnet = seeded_unet(d, hd, 5), seeded_mnet(d, hm, 6, 0.1)
     gam = {"gamma": torch.tensor([6.0]), "gamma2": torch.tensor([1.0]), "gamma3": torch.tensor([1.0])}
-    noises = torch.randn(K, B, d, generator=torch.Generator().manual_seed(2)).to(DEV)
+    sde = make_product_sde(st, unet, mnet, gam, hd, hm, DEV)
+    noises = gpu_kink_free_noise(sde, torch.zeros(d, device=DEV), torch.linspace(0, 1.0, K + 1, device=DEV), B, seed=2)
     res = []
     for ffma in (True, False):
         sde = make_product_sde(st, unet, mnet, gam, hd, hm, DEV)
@@ -140,7 +141,7 @@ def test_tc_k3_is_the_default_for_large_batches_and_agrees_with_ffma():
     (l0, g0), (l1, g1) = res
     assert abs(l0 - l1) <= 1e-5 * abs(l0)
     for n in g0:
-        assert rel_l2(g1[n], g0[n]) <= 2e-3, (n, rel_l2(g1[n], g0[n]))
+        assert rel_l2(g1[n], g0[n]) <= 1e-4, (n, rel_l2(g1[n], g0[n]))
 
 
 @pytest.mark.parametrize("d,K,B", [(10, 200, 300), (1, 150, 64), (20, 50, 129), (3, 7, 5)])
@@ -205,8 +206,8 @@ def test_target_gemm_bwd_tc_matches_fp64(d, K, B):
                                                         ("molecular_dynamics", 1, 150, 200, False, True)])
 def test_tc_k3_general_loss_paths_agree_with_ffma(kind, d, K, B, dense, stopping):
     """Dense sigma (generic per-point loss inside K3a) and stopping-time masks (per-point stop indicator,
-    Z = sum of indicators) through the tcgen05 K3: loss 1e-5 and gradients 2e-3 against the fp32 FFMA
-    kernels on the same injected noise (gradient bound: ReLU-mask flips, see the module docstring)."""
+    Z = sum of indicators) through the tcgen05 K3: loss 1e-5 and every gradient tensor 1e-4 against the fp32 FFMA
+    kernels on the same kink-free injected noise."""
     import soc_matching_b200 as sb
     st = random_setting(kind, d, seed=d + K, dense_sigma=dense)
     hd, hm = [256, 128, 64], [64, 64]
@@ -214,7 +215,8 @@ def test_tc_k3_general_loss_paths_agree_with_ffma(kind, d, K, B, dense, stopping
     mnet = seeded_mnet(d, hm, 42 + d, 0.1, 3 if stopping else 2)
     gam = {"gamma": torch.tensor([2.0]), "gamma2": torch.tensor([1.0]), "gamma3": torch.tensor([1.0])}
     x0 = -torch.ones(d) if stopping else 0.3 * torch.ones(d)
-    noises = torch.randn(K, B, d, generator=torch.Generator().manual_seed(7)).to(DEV)
+    sde = make_product_sde(st, unet, mnet, gam, hd, hm, DEV, stopping=stopping)
+    noises = gpu_kink_free_noise(sde, x0.to(DEV), torch.linspace(0, 1.0, K + 1, device=DEV), B, seed=7)
     res = []
     for tc_path in (False, True):
         sde = make_product_sde(st, unet, mnet, gam, hd, hm, DEV, stopping=stopping)
@@ -229,15 +231,13 @@ def test_tc_k3_general_loss_paths_agree_with_ffma(kind, d, K, B, dense, stopping
     assert torch.equal(s0, s1)                                   # stopping indicators (tcgen05 vs FFMA rollout)
     assert abs(l0 - l1) <= 1e-5 * abs(l0), (l0, l1)
     for n in g0:
-        assert rel_l2(g1[n], g0[n]) <= 2e-3, (n, rel_l2(g1[n], g0[n]))
+        assert rel_l2(g1[n], g0[n]) <= 1e-4, (n, rel_l2(g1[n], g0[n]))
 
 
 def test_full_chunk_tc_iteration_agrees_with_fp32_ffma():
     """BASELINE config 5 at the size of one bench chunk (double_well d=10, K=200, B=75 776 paths = 15.2 M
-    trajectory points, Philox noise): the tcgen05 path (rollout, target GEMMs, K3) against the exact-fp32 FFMA /
-    SIMT path on the same Philox key.  Loss 1e-5; gradient tensors 2e-4: measured 1.2e-4 on the two 64-wide
-    bottleneck layers and <= 5e-5 elsewhere (scripts/path_precision.py attributes it to K3: the SOCM residual
-    nabla_V - target cancels for those layers and amplifies the 3xTF32 chain's 3e-5, see the next test)."""
+    trajectory points): the tcgen05 path (rollout, target GEMMs, K3) against the exact-fp32 FFMA / SIMT path on the
+    same kink-free injected noise.  Loss 1e-5, every gradient tensor 1e-4 (north star)."""
     import soc_matching_b200 as sb
     from soc_matching_b200 import simulate
     d, K, B = 10, 200, 75776
@@ -246,13 +246,15 @@ def test_full_chunk_tc_iteration_agrees_with_fp32_ffma():
     unet, mnet = seeded_unet(d, hd, 5), seeded_mnet(d, hm, 6, 0.1)
     gam = {"gamma": torch.tensor([6.0]), "gamma2": torch.tensor([1.0]), "gamma3": torch.tensor([1.0])}
     res = []
+    sde = make_product_sde(st, unet, mnet, gam, hd, hm, DEV)
+    noises = gpu_kink_free_noise(sde, torch.zeros(d, device=DEV), torch.linspace(0, 1.0, K + 1, device=DEV), B, seed=77)
+    del sde
     for ffma in (True, False):
-        torch.manual_seed(1234)
-        simulate._SEED_COUNTER[0] = 77            # same Philox key for both runs
         sde = make_product_sde(st, unet, mnet, gam, hd, hm, DEV)
         solver = sb.SOC_Solver(sde, torch.zeros(d, device=DEV), None, T=1.0, num_steps=K, lmbd=1.0, d=d,
                                sigma=sde.sigma)
         solver.force_ffma = ffma
+        solver.inject_noise(noises)
         out = solver.loss(B, algorithm="SOCM")
         out[0].backward()
         res.append((float(out[0].detach()), float(out[5]), out[7].clone(),
@@ -263,8 +265,10 @@ def test_full_chunk_tc_iteration_agrees_with_fp32_ffma():
     assert abs(l1 - l0) <= 1e-5 * abs(l0), (l0, l1)
     assert abs(w1 - w0) <= 1e-5 * abs(w0)
     assert torch.equal(s0, s1)
+    errs = {n: rel_l2(g1[n], g0[n]) for n in g0}
+    print("full chunk, tcgen05 vs fp32 FFMA, per-tensor gradient error:", {k: f"{v:.1e}" for k, v in errs.items()})
     for n in g0:
-        assert rel_l2(g1[n], g0[n]) <= 2e-4, (n, rel_l2(g1[n], g0[n]))
+        assert errs[n] <= 1e-4, (n, errs[n])
 
 
 def test_full_chunk_k3_tc_against_fp64_autograd():
