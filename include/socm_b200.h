@@ -105,6 +105,31 @@ int socm_rollout_f32(const socm_setting* st, const socm_unet* net, const socm_wa
                      float* logw_det, float* logw_sto, float* logw_term,
                      void* workspace, uint32_t flags, void* stream);
 
+/* The same rollout under a TABULATED control instead of the network: the `else` branch of NeuralSDE.control
+ * (method.py:103-107) with the ground-truth controls of models.py:10-150, as used by control_objective /
+ * normalization_constant on the optimal SDE (utils.py:131-231, main.py:117-153).
+ *   SOCM_CONTROL_AFFINE  u_k(x) = A_k x + c_k, rows k = 0..K-1 tabulated by the caller on the grid times:
+ *                        LinearControl (models.py:10-39)          A_k = u[floor((n-1) t_k / T)],  c = NULL
+ *                        ConstantControlLinear (models.py:61-81)  A = NULL,  c_k = ut[floor(n t_k / T)]
+ *   SOCM_CONTROL_LOOKUP  LowDimControl (models.py:84-150): u_j = ut[idx_t[k]][clamp(floor((x_j + xb) / dx), 0, nx-1)][j],
+ *                        idx_t[k] = ceil(t_k / delta_t) tabulated by the caller, ut[nt][nx][d]. */
+#define SOCM_CONTROL_AFFINE 0
+#define SOCM_CONTROL_LOOKUP 1
+typedef struct {
+  int32_t kind;
+  const float* A;       /* [K][d][d] or NULL */
+  const float* c;       /* [K][d]    or NULL */
+  const float* ut;      /* [nt][nx][d] */
+  const int32_t* idx_t; /* [K] */
+  int32_t nx;
+  float xb, dx;
+} socm_tab_control;
+int socm_rollout_tabulated_f32(const socm_setting* st, const socm_tab_control* ctrl, const float* x0,
+                               const float* step_tab, const float* noise_in, uint64_t seed, uint64_t path_offset,
+                               int32_t B, int32_t K, float* states, float* noises, float* controls, float* stop,
+                               float* eff_dt, float* logw_det, float* logw_sto, float* logw_term, uint32_t flags,
+                               void* stream);
+
 /* Philox4x32-10 + Box-Muller exactly as the rollout draws it: out[k][m][j]. */
 int socm_philox_normal_f32(uint64_t seed, uint64_t path_offset, int32_t B, int32_t K, int32_t d,
                            float* out, void* stream);
@@ -176,6 +201,24 @@ typedef struct socm_adam_tensor {
 } socm_adam_tensor;
 int socm_adam_step_f32(const socm_adam_tensor* tensors /* host array */, int32_t n_tensors, double beta1, double beta2,
                        double eps, int32_t step, int32_t zero_grad, void* stream);
+
+/* One launch for the per-iteration statistics of the reference's training loop (main.py:325-393, compute_EMA of
+ * utils.py:389-396): squared norm of the control network's gradient, the EMA of every gradient tensor (updated in
+ * place) and its squared norm, and the EMAs of loss / mean(w) / std(w) plus the running normalisation constant
+ * (EMA of mean(w) with its own coefficient, main.py:354-359).
+ *   scalars (device, fp32[3]): loss, mean(w), std(w) of this iteration
+ *   stats   (device, fp32[8], in/out): 0 grad_norm_sqd  1 EMA_grad_norm_sqd  2 sqd_norm_EMA_grad  3 EMA_loss
+ *                                      4 EMA_weight_mean  5 EMA_weight_std  6 normalization_const  7 unused
+ *   scratch (device, 32 bytes, zeroed once by the caller; the kernel leaves it zeroed)
+ *   itr = 0-based iteration index (selects the warm-up rule of compute_EMA). */
+typedef struct socm_ema_tensor {
+  const float* grad;
+  float* ema_grad;
+  int64_t n;
+} socm_ema_tensor;
+int socm_ema_stats_f32(const socm_ema_tensor* tensors /* host array */, int32_t n_tensors, const float* scalars,
+                       float* stats, void* scratch, int32_t itr, double ema_coeff, double ema_weight_mean_coeff,
+                       void* stream);
 
 /* --- K3: UNet forward at all (K+1)B points + weighted loss + backward
  *     (replaces method.py:272-287, 692-720 and loss.backward(), main.py:323) -------------

@@ -38,9 +38,20 @@ class AdamTensor(C.Structure):
                 ("n", C.c_int64), ("lr", C.c_float)]
 
 
+class EmaTensor(C.Structure):
+    """socm_ema_tensor"""
+    _fields_ = [("grad", C.c_void_p), ("ema_grad", C.c_void_p), ("n", C.c_int64)]
+
+
 class WarmTable(C.Structure):
     """socm_warm_table"""
     _fields_ = [("A", C.c_void_p), ("c", C.c_void_p)]
+
+
+class TabControl(C.Structure):
+    """socm_tab_control"""
+    _fields_ = [("kind", C.c_int32), ("A", C.c_void_p), ("c", C.c_void_p), ("ut", C.c_void_p), ("idx_t", C.c_void_p),
+                ("nx", C.c_int32), ("xb", C.c_float), ("dx", C.c_float)]
 
 
 # name -> (restype, argtypes); must list every symbol include/socm_b200.h declares
@@ -52,6 +63,8 @@ PROTOTYPES = {
     "socm_rollout_workspace_bytes": (_i64, [C.POINTER(UNet)]),
     "socm_rollout_f32": (C.c_int, [C.POINTER(Setting), C.POINTER(UNet), C.POINTER(WarmTable), _vp, _vp, _vp,
                                    _u64, _u64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
+    "socm_rollout_tabulated_f32": (C.c_int, [C.POINTER(Setting), C.POINTER(TabControl), _vp, _vp, _vp, _u64, _u64, _i32,
+                                             _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
     "socm_philox_normal_f32": (C.c_int, [_u64, _u64, _i32, _i32, _i32, _vp, _vp]),
     "socm_unet_forward_f32": (C.c_int, [C.POINTER(UNet), _vp, _i32, _vp, _vp]),
     "socm_target_prep_f32": (C.c_int, [C.POINTER(Setting), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp,
@@ -67,6 +80,7 @@ PROTOTYPES = {
     "socm_target_grouped_bwd_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "socm_target_adjoint_f32": (C.c_int, [C.POINTER(Setting), _vp, _i32, _i32, _f32, _vp, _i32, _vp]),
     "socm_adam_step_f32": (C.c_int, [C.POINTER(AdamTensor), _i32, C.c_double, C.c_double, C.c_double, _i32, _i32, _vp]),
+    "socm_ema_stats_f32": (C.c_int, [C.POINTER(EmaTensor), _i32, _vp, _vp, _vp, _i32, C.c_double, C.c_double, _vp]),
     "socm_loss_workspace_bytes": (_i64, [C.POINTER(UNet), _i32, _i32]),
     "socm_unet_param_count": (_i64, [C.POINTER(UNet)]),
     "socm_unet_loss_fwdbwd_f32": (C.c_int, [C.POINTER(Setting), C.POINTER(UNet), C.POINTER(WarmTable), _vp, _vp,
@@ -82,6 +96,7 @@ DEBUG_PROTOTYPES = {
 ROLLOUT_FORCE_GENERIC = 1
 ROLLOUT_NO_TRAJ = 2
 ROLLOUT_FORCE_FFMA = 4
+CONTROL_AFFINE, CONTROL_LOOKUP = 0, 1
 LOSS_FORCE_GENERIC = 1
 LOSS_FORCE_FFMA = 2
 LOSS_FORCE_TC = 4

@@ -247,8 +247,9 @@ __device__ __forceinline__ float sde_step(const socm_setting& st, const float* w
                                           float sq_dtl, PathAcc& acc) {
   const int d = st.d;
   float tmp[kMaxDim], se[kMaxDim];
-  // u = -sigma^T nabla_V (method.py:68-72)
-  if (st.sigma_is_identity) {
+  // u = -sigma^T nabla_V (method.py:68-72); gv == nullptr: u already holds the control (tabulated u, method.py:103-107)
+  if (gv == nullptr) {
+  } else if (st.sigma_is_identity) {
     for (int i = 0; i < d; ++i) u[i] = -gv[i * ldv];
   } else {
     for (int i = 0; i < d; ++i) {

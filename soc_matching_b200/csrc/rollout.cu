@@ -137,6 +137,63 @@ __global__ void __launch_bounds__(tile::NT, 1) rollout_tile_kernel(RolloutArgs a
   }
 }
 
+// ---------------------------------------------------------------- rollout under a TABULATED control (no network)
+// The ground-truth / baseline controls of models.py:10-150, consumed by control_objective and normalization_constant
+// (utils.py:131-231, main.py:117-153) through the `else` branch of NeuralSDE.control (method.py:103-107):
+//   affine  u_k(x) = A_k x + c_k   LinearControl (models.py:10-39: A_k = u[floor((n-1) t_k / T)], c = 0) and
+//                                  ConstantControlLinear (models.py:61-81: A = 0, c_k = ut[floor(n t_k / T)]);
+//                                  the caller tabulates A_k, c_k on the grid times with the reference's index rule
+//   lookup  u_j(t_k, x) = ut[it_k][clamp(floor((x_j + xb) / dx), 0, nx - 1)][j]      LowDimControl (models.py:84-150),
+//                                  it_k = ceil(t_k / delta_t) tabulated by the caller
+// One thread per path, state in registers / local memory; the SDE step, stopping logic and weight accumulation are the
+// shared sde_step of common.cuh, so every output has the semantics of utils.py:17-128.
+__global__ void __launch_bounds__(128) rollout_tab_kernel(RolloutArgs a, socm_tab_control c) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= a.B) return;
+  const int d = a.st.d, K = a.K;
+  float x[kMaxDim], u[kMaxDim], eps[kMaxDim];
+  PathAcc acc{1.f, 0.f, 0.f};
+  for (int j = 0; j < d; ++j) {
+    x[j] = __ldg(a.x0 + (size_t)m * d + j);
+    if (a.states) a.states[(size_t)m * d + j] = x[j];
+  }
+  if (a.stop) a.stop[m] = 1.f;
+  for (int k = 0; k < K; ++k) {
+    if (c.kind == SOCM_CONTROL_AFFINE) {
+      for (int i = 0; i < d; ++i) {
+        float v = c.c ? __ldg(c.c + (size_t)k * d + i) : 0.f;
+        if (c.A)
+          for (int j = 0; j < d; ++j) v = fmaf(__ldg(c.A + ((size_t)k * d + i) * d + j), x[j], v);
+        u[i] = v;
+      }
+    } else {
+      const int it = __ldg(c.idx_t + k);
+      for (int j = 0; j < d; ++j) {
+        // floor((x + xb) / delta_x) clamped to the table (models.py:97-105), same fp32 operations
+        int ix = (int)floorf(__fdiv_rn(__fadd_rn(x[j], c.xb), c.dx));
+        ix = ix < 0 ? 0 : (ix > c.nx - 1 ? c.nx - 1 : ix);
+        u[j] = __ldg(c.ut + ((size_t)it * c.nx + ix) * d + j);
+      }
+    }
+    draw_noise(a, m, k, eps);
+    const float dt = __ldg(a.step_tab + k), sq_ldt = __ldg(a.step_tab + K + k);
+    const float dt_l = __ldg(a.step_tab + 2 * K + k), sq_dtl = __ldg(a.step_tab + 3 * K + k);
+    const float eff = sde_step(a.st, nullptr, nullptr, x, 1, nullptr, 1, eps, u, dt, sq_ldt, dt_l, sq_dtl, acc);
+    const size_t row = (size_t)k * a.B + m;
+    if (a.states) {
+      for (int j = 0; j < d; ++j) {
+        a.states[(row + a.B) * d + j] = x[j];
+        a.controls[row * d + j] = u[j];
+      }
+      if (a.noise_in == nullptr)
+        for (int j = 0; j < d; ++j) a.noises[row * d + j] = eps[j];
+      a.stop[row + a.B] = acc.alive;
+      a.eff_dt[row] = eff;
+    }
+  }
+  path_finish(a, m, x, 1, acc);
+}
+
 // ---------------------------------------------------------------- Philox noise as a stand-alone op
 __global__ void philox_normal_kernel(uint64_t seed, uint64_t path_offset, int B, int K, int d, float* out) {
   const int nblk = (d + 3) / 4;
@@ -235,6 +292,50 @@ extern "C" int socm_rollout_f32(const socm_setting* st, const socm_unet* net, co
     rollout_generic_kernel<<<(B + warps - 1) / warps, warps * 32, smem, stream>>>(a, *net);
     SOCM_LAUNCH_CHECK();
   }
+  return SOCM_OK;
+}
+
+extern "C" int socm_rollout_tabulated_f32(const socm_setting* st, const socm_tab_control* ctrl, const float* x0,
+                                          const float* step_tab, const float* noise_in, uint64_t seed,
+                                          uint64_t path_offset, int32_t B, int32_t K, float* states, float* noises,
+                                          float* controls, float* stop, float* eff_dt, float* logw_det,
+                                          float* logw_sto, float* logw_term, uint32_t flags, void* stream_) {
+  if (int rc = validate_setting(st)) return rc;
+  SOCM_CHECK_ARG(ctrl != nullptr, "control table is NULL");
+  SOCM_CHECK_ARG(B >= 0 && K >= 1, "bad sizes B=%d K=%d", B, K);
+  SOCM_CHECK_ARG(x0 && step_tab && logw_det && logw_sto && logw_term, "required pointer is NULL");
+  const bool no_traj = flags & SOCM_ROLLOUT_NO_TRAJ;
+  SOCM_CHECK_ARG(no_traj || (states && controls && stop && eff_dt && (noises || noise_in)),
+                 "trajectory outputs are NULL (pass SOCM_ROLLOUT_NO_TRAJ for weights-only mode)");
+  if (ctrl->kind == SOCM_CONTROL_AFFINE) {
+    SOCM_CHECK_ARG(ctrl->A || ctrl->c, "affine control needs A and / or c");
+  } else if (ctrl->kind == SOCM_CONTROL_LOOKUP) {
+    SOCM_CHECK_ARG(ctrl->ut && ctrl->idx_t && ctrl->nx >= 1 && ctrl->dx > 0.f, "lookup control needs ut, idx_t, nx, dx");
+  } else {
+    set_error("unknown control kind %d", ctrl->kind);
+    return SOCM_ERR_UNSUPPORTED;
+  }
+  if (B == 0) return SOCM_OK;
+  RolloutArgs a;
+  a.st = *st;
+  a.warmA = a.warmc = nullptr;
+  a.x0 = x0;
+  a.step_tab = step_tab;
+  a.noise_in = noise_in;
+  a.seed = seed;
+  a.path_offset = path_offset;
+  a.B = B;
+  a.K = K;
+  a.states = no_traj ? nullptr : states;
+  a.noises = noises;
+  a.controls = controls;
+  a.stop = no_traj ? nullptr : stop;
+  a.eff_dt = eff_dt;
+  a.lw_det = logw_det;
+  a.lw_sto = logw_sto;
+  a.lw_term = logw_term;
+  rollout_tab_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream_)>>>(a, *ctrl);
+  SOCM_LAUNCH_CHECK();
   return SOCM_OK;
 }
 

@@ -67,10 +67,12 @@ class RolloutWorkspace:
         else:
             self.states = self.noises = self.controls = self.stop = self.eff_dt = None
         self.lw = torch.empty(3, B, **f32)
-        udesc, keep = networks.unet_desc(net)
-        nbytes = _lib.load().socm_rollout_workspace_bytes(udesc)
-        self.packed = torch.empty((nbytes + 3) // 4, **f32)
-        del keep
+        self.packed = None
+        if net is not None:      # packed weight tape of the control network (none under a tabulated control)
+            udesc, keep = networks.unet_desc(net)
+            nbytes = _lib.load().socm_rollout_workspace_bytes(udesc)
+            self.packed = torch.empty((nbytes + 3) // 4, **f32)
+            del keep
 
 
 def rollout(sde, x0: torch.Tensor, t: torch.Tensor, lmbd: float, *, noises: Optional[torch.Tensor] = None,
@@ -82,15 +84,12 @@ def rollout(sde, x0: torch.Tensor, t: torch.Tensor, lmbd: float, *, noises: Opti
     ``force_generic`` / other hdims -> shape-generic warp-per-path kernel."""
     lib = _lib.load()
     _lib.require_cuda(x0, "x0")
-    if not getattr(sde, "use_learned_control", False):
-        raise NotImplementedError(
-            "only the learned control (sde.use_learned_control=True, UNet nabla_V) runs on the fused rollout; "
-            "tabulated ground-truth controls are not ported yet (SURVEY.md section 8f row 1)"
-        )
     desc = desc or describe_setting(sde, x0.device)
     B, K = int(x0.shape[0]), int(t.shape[0]) - 1
     if desc.lmbd != float(lmbd):
         desc.c_struct.lmbd = float(lmbd)
+    if not getattr(sde, "use_learned_control", False):
+        return _rollout_tabulated(lib, sde, desc, x0, t, lmbd, noises, seed, path_offset, store_traj, workspace, timer)
     ws = workspace or RolloutWorkspace(desc, sde.nabla_V, B, K, x0.device, store_traj)
     udesc, keep = networks.unet_desc(sde.nabla_V)
     tab = step_table(t.to(x0.device), float(lmbd))
@@ -122,6 +121,38 @@ def rollout(sde, x0: torch.Tensor, t: torch.Tensor, lmbd: float, *, noises: Opti
         timer("rollout", n_k, lib.socm_rollout_f32, *args)
     else:
         _lib.check(lib.socm_rollout_f32(*args))
+    del keep
+    return ws
+
+
+def _rollout_tabulated(lib, sde, desc, x0, t, lmbd, noises, seed, path_offset, store_traj, workspace, timer):
+    """method.py:103-107: ``sde.u`` is a tabulated ground-truth control (models.py:10-150), no network in the loop."""
+    from . import controls
+    if getattr(sde, "u", None) is None:
+        raise NotImplementedError("sde.use_learned_control is False and sde.u is None: there is no control to roll out")
+    B, K, d = int(x0.shape[0]), int(t.shape[0]) - 1, desc.d
+    ws = workspace or RolloutWorkspace(desc, None, B, K, x0.device, store_traj)
+    ctrl, keep = controls.tabulate(sde.u, t, d, x0.device)
+    tab = step_table(t.to(x0.device), float(lmbd))
+    x0c = x0.detach().float().contiguous()
+    noise_ptr = None
+    if noises is not None:
+        _lib.require_cuda(noises, "noises")
+        noises = noises.detach().float().contiguous()
+        assert tuple(noises.shape) == (K, B, d), f"noises must be (K,B,d), got {tuple(noises.shape)}"
+        noise_ptr = noises.data_ptr()
+        if store_traj:
+            ws.noises = noises
+    if B == 0:
+        return ws
+    args = (desc.c_struct, ctrl, _lib.ptr(x0c), _lib.ptr(tab), noise_ptr, next_seed() if seed is None else seed,
+            path_offset, B, K, _lib.ptr(ws.states), _lib.ptr(ws.noises), _lib.ptr(ws.controls), _lib.ptr(ws.stop),
+            _lib.ptr(ws.eff_dt), ws.lw[0].data_ptr(), ws.lw[1].data_ptr(), ws.lw[2].data_ptr(),
+            0 if store_traj else _lib.ROLLOUT_NO_TRAJ, _lib.stream_ptr())
+    if timer is not None:
+        timer("rollout", 1, lib.socm_rollout_tabulated_f32, *args)
+    else:
+        _lib.check(lib.socm_rollout_tabulated_f32(*args))
     del keep
     return ws
 

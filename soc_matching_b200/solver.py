@@ -233,7 +233,9 @@ class SOC_Solver(nn.Module):
         scale = 1.0 if stopping else 1.0 / ((K + 1) * B)                    # method.py:715 / 720
         warm_struct = simulate._warm_struct(warm_loss.A_loss, warm_loss.c_loss) if warm_loss is not None else None
         k2_ws = None          # workspace of the tcgen05 target GEMM
-        simt_target = self.force_ffma or self.force_generic or self.force_simt_target
+        # the tcgen05 target GEMM gives one CTA 128 paths and streams the whole table through it: below ~1k paths
+        # most SMs would idle (0.72 ms at B = 128 vs 0.03 ms for the SIMT GEMM, whose grid tiles rows x paths)
+        simt_target = self.force_ffma or self.force_generic or self.force_simt_target or B < 1024
         k2b_ws, k2b_nb = None, -1
 
         x0_rep = self.x0.detach().float().reshape(1, d)
