@@ -88,6 +88,8 @@ int socm_device_info(int* sm_count, int* smem_optin_bytes);
 #define SOCM_ROLLOUT_FORCE_GENERIC 1u /* use the shape-generic kernel even for the default net */
 #define SOCM_ROLLOUT_NO_TRAJ 2u       /* weights-only mode: states/noises/controls may be NULL */
 #define SOCM_ROLLOUT_FORCE_FFMA 4u    /* default net: use the fp32 FFMA tile kernel instead of tcgen05 (3xTF32) */
+#define SOCM_ROLLOUT_F16 8u           /* default net, d <= 15: fp16-split tcgen05 engine, two CTAs per SM (unet_h.cuh) */
+#define SOCM_ROLLOUT_TF32 16u         /* default net: the 3xTF32 tcgen05 engine even where the fp16-split one is the default */
 
 /* step_tab: [5][K] = dt_k, sqrt(lmbd*dt_k), dt_k/lmbd, sqrt(dt_k/lmbd), t_k  computed by the
  *           caller in fp32 exactly like utils.py:38,47,95-98 (dt from the fp32 linspace).

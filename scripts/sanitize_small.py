@@ -13,7 +13,7 @@ import soc_matching_b200 as sb
 DEV = "cuda"
 hd = [256, 128, 64]
 gam = {"gamma": torch.tensor([2.0]), "gamma2": torch.tensor([1.0]), "gamma3": torch.tensor([1.0])}
-for kind, d, K, B, stopping, flags in [("double_well", 10, 6, 130, False, ("tc",)), ("double_well", 10, 6, 130, False, ("ffma",)),
+for kind, d, K, B, stopping, flags in [("double_well", 10, 40, 130, False, ("tc",)), ("double_well", 10, 40, 130, False, ("ffma",)),
                                        ("ou_quadratic", 20, 4, 70, False, ("tc",)), ("molecular_dynamics", 1, 12, 140, True, ("tc",))]:
     st = random_setting(kind, d, seed=1)
     hm = [64, 64] if stopping else [128, 128]
@@ -22,8 +22,8 @@ for kind, d, K, B, stopping, flags in [("double_well", 10, 6, 130, False, ("tc",
     x0 = (-torch.ones(d) if stopping else torch.zeros(d)).to(DEV)
     solver = sb.SOC_Solver(sde, x0, None, T=1.0, num_steps=K, lmbd=1.0, d=d, sigma=sde.sigma)
     solver.force_tc, solver.force_ffma = "tc" in flags, "ffma" in flags
-    opt = sb.FusedAdam([{"params": list(sde.nabla_V.parameters())}, {"params": list(sde.M.sigmoid_layers.parameters()), "lr": 1e-2}],
-                       lr=1e-4)
+    opt = sb.FusedAdam([{"params": list(sde.nabla_V.parameters())}, {"params": list(sde.M.sigmoid_layers.parameters()), "lr": 1e-4}],
+                       lr=1e-5)
     tr = sb.Trainer(solver, opt, "SOCM", B, normalization_const=1.0, use_stopping_time=stopping)
     for itr in range(2):
         loss, wm, ws = tr.step(itr)

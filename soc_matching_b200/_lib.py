@@ -96,6 +96,8 @@ DEBUG_PROTOTYPES = {
 ROLLOUT_FORCE_GENERIC = 1
 ROLLOUT_NO_TRAJ = 2
 ROLLOUT_FORCE_FFMA = 4
+ROLLOUT_F16 = 8
+ROLLOUT_TF32 = 16
 CONTROL_AFFINE, CONTROL_LOOKUP = 0, 1
 LOSS_FORCE_GENERIC = 1
 LOSS_FORCE_FFMA = 2

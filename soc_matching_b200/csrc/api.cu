@@ -1,5 +1,6 @@
 // api.cu -- bookkeeping entry points of the C ABI (include/socm_b200.h) and shared host helpers.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -49,6 +50,14 @@ int validate_unet(const socm_unet* net, int d) {
 }
 
 bool is_default_arch(const socm_unet* net) { return net->h0 == 256 && net->h1 == 128 && net->h2 == 64; }
+
+int f16_default() {
+  static const int v = [] {
+    const char* e = getenv("SOCM_F16");
+    return e == nullptr ? -1 : (e[0] == '1' ? 1 : 0);
+  }();
+  return v;
+}
 
 int sm_count() {
   static thread_local int cached_dev = -1, cached = 0;

@@ -43,6 +43,7 @@ void set_error(const char* fmt, ...);
 int validate_setting(const socm_setting* st);
 int validate_unet(const socm_unet* net, int d);
 bool is_default_arch(const socm_unet* net);  // hdims == [256,128,64]
+int f16_default();                           // SOCM_F16 environment switch: 1 / 0 force the fp16-split / 3xTF32 engine, -1 unset
 int sm_count();
 
 // ---------------------------------------------------------------- Philox4x32-10

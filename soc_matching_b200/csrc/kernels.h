@@ -20,4 +20,10 @@ int launch_wgrad_tc(const unsigned char* scratch, int n_tiles, int d, float* gra
 bool loss_tc_supported(const socm_unet* net);
 int64_t loss_tc_workspace_bytes(int d, int B, int K);
 }  // namespace tc
+namespace hx {
+// fp16-split tcgen05 engine, two CTAs per SM (unet_h.cuh): default hdims and d <= 15
+bool rollout_h_supported(const socm_unet* net);
+int64_t rollout_h_workspace_bytes();
+int launch_rollout_h(const RolloutArgs& a, const socm_unet* net, void* workspace, cudaStream_t stream);
+}  // namespace hx
 }  // namespace socm

@@ -232,7 +232,8 @@ using namespace socm;
 extern "C" int64_t socm_rollout_workspace_bytes(const socm_unet* net) {
   if (!net) return -1;
   const int64_t ffma = tile::packed_floats(net->d) * (int64_t)sizeof(float);
-  const int64_t tcb = tc::rollout_tc_supported(net) ? tc::rollout_tc_workspace_bytes(net->d) : 0;
+  int64_t tcb = tc::rollout_tc_supported(net) ? tc::rollout_tc_workspace_bytes(net->d) : 0;
+  if (hx::rollout_h_supported(net) && hx::rollout_h_workspace_bytes() > tcb) tcb = hx::rollout_h_workspace_bytes();
   return ffma > tcb ? ffma : tcb;
 }
 
@@ -271,7 +272,14 @@ extern "C" int socm_rollout_f32(const socm_setting* st, const socm_unet* net, co
   a.lw_sto = logw_sto;
   a.lw_term = logw_term;
 
-  if (tc::rollout_tc_supported(net) && !(flags & (SOCM_ROLLOUT_FORCE_GENERIC | SOCM_ROLLOUT_FORCE_FFMA))) {
+  // fp16-split engine (two CTAs per SM) once there is more than one 128-path tile per SM; a single resident tile per
+  // SM has a shorter step on the 3xTF32 engine (fewer hand-offs).  SOCM_F16=1 / 0 in the environment forces either.
+  const bool want_f16 = (flags & SOCM_ROLLOUT_F16) || f16_default() == 1 ||
+                        (f16_default() < 0 && (B + 127) / 128 > sm_count());
+  if (want_f16 && hx::rollout_h_supported(net) && !(flags & (SOCM_ROLLOUT_FORCE_GENERIC | SOCM_ROLLOUT_FORCE_FFMA | SOCM_ROLLOUT_TF32))) {
+    SOCM_CHECK_ARG(workspace != nullptr, "workspace is NULL (socm_rollout_workspace_bytes)");
+    if (int rc = hx::launch_rollout_h(a, net, workspace, stream)) return rc;
+  } else if (tc::rollout_tc_supported(net) && !(flags & (SOCM_ROLLOUT_FORCE_GENERIC | SOCM_ROLLOUT_FORCE_FFMA))) {
     SOCM_CHECK_ARG(workspace != nullptr, "workspace is NULL (socm_rollout_workspace_bytes)");
     if (int rc = tc::launch_rollout_tc(a, net, workspace, stream)) return rc;
   } else if (is_default_arch(net) && !(flags & SOCM_ROLLOUT_FORCE_GENERIC)) {

@@ -11,6 +11,7 @@
 // so one buffer of "[point][feature]" activations serves the forward/dgrad GEMMs (K = features)
 // and the weight-gradient GEMMs (K = points) without a transpose.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -32,7 +33,28 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn, int b_
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::f16 (fp16 operands, fp32 accumulation): K = 16 per instruction.  Shared-memory operands use the same canonical
+// no-swizzle layout with 16-byte core-matrix rows = 8 halfs; an A operand in tensor memory holds two halfs per 32-bit
+// column, the even k in the low half (conventions measured with scripts/f16_probe.cu, profiles/r2_f16_probe.log).
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // ---------------------------------------------------------------- MMA issue (one thread)
+__device__ __forceinline__ void mma_ss_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 // D[tmem] (+)= A[smem] * B[smem]
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -141,6 +163,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or the limit (ns) expires,
+// instead of returning to a software spin loop after the short default.  With two CTAs per SM the spinning warps
+// (MMA issuer, tape producer, epilogue warps between phases) otherwise take ~40 % of all issue slots away from the
+// warps that have work (ncu, first fp16 rollout kernel: BRA + SYNCS + YIELD = 39 % of executed instructions).
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_addr(bar)), "r"(parity), "r"(100000u)
+        : "memory");
+  } while (ok == 0);
+}
 // 1-D bulk copy global -> shared through the TMA engine (SASS UBLKCP), completion on an mbarrier
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -154,6 +192,25 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // is exact in fp32.  x*y ~= hi_x*hi_y + lo_x*hi_y + hi_x*lo_y  (error ~2^-21 |x y|).
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
+
+// ---------------------------------------------------------------- fp16 hi / lo split ("2xFP16": x ~ hi + lo, 22 bits)
+// two floats -> packed f16x2 (first argument in the LOW half), round to nearest, saturating to +-65504
+__device__ __forceinline__ uint32_t pack_h2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+// f16x2 -> two floats through the FP16 pipe (HADD2.F32 with a half selector; a plain cvt.f32.f16 of the upper half
+// compiles to the slow F2F conversion unit)
+__device__ __forceinline__ float2 h2_to_f2(uint32_t h) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&h));
+}
+// (a, b) -> hi = f16x2(a, b), lo = f16x2(a - hi.a, b - hi.b)
+__device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_h2(a, b);
+  const float2 f = h2_to_f2(hi);
+  lo = pack_h2(a - f.x, b - f.y);
+}
 
 // true in exactly one lane of a fully converged warp (the same lane every time)
 __device__ __forceinline__ bool elect_one() {

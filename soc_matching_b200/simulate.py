@@ -11,6 +11,9 @@ from . import _lib, networks
 from .sde import SettingDesc, describe_setting
 
 _SEED_COUNTER = [0]
+# tensor-core engine of the default-width kernels: None = library default (SOCM_F16 environment switch),
+# "f16" = fp16-split engine with two CTAs per SM (csrc/unet_h.cuh, d <= 15), "tf32" = 3xTF32 engine (csrc/unet_tc.cuh)
+ENGINE = None
 
 
 def step_table(t: torch.Tensor, lmbd: float) -> torch.Tensor:
@@ -97,7 +100,8 @@ def rollout(sde, x0: torch.Tensor, t: torch.Tensor, lmbd: float, *, noises: Opti
     warm = resolve_warm_start(sde, t)
     wstruct = _warm_struct(warm.A_roll, warm.c_roll) if warm is not None else None
     flags = ((0 if store_traj else _lib.ROLLOUT_NO_TRAJ) | (_lib.ROLLOUT_FORCE_GENERIC if force_generic else 0)
-             | (_lib.ROLLOUT_FORCE_FFMA if force_ffma else 0))
+             | (_lib.ROLLOUT_FORCE_FFMA if force_ffma else 0)
+             | {None: 0, "f16": _lib.ROLLOUT_F16, "tf32": _lib.ROLLOUT_TF32}[ENGINE])
     noise_ptr = None
     if noises is not None:
         _lib.require_cuda(noises, "noises")

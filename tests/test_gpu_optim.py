@@ -106,8 +106,11 @@ def test_trainer_step_runs_the_loop_body():
     st = random_setting("double_well", d, seed=2)
     gam = {"gamma": torch.tensor([6.0]), "gamma2": torch.tensor([1.0]), "gamma3": torch.tensor([1.0])}
     sde = make_product_sde(st, seeded_unet(d, hd, 1), seeded_mnet(d, hm, 2), gam, hd, hm, DEV)
-    solver = sb.SOC_Solver(sde, torch.zeros(d, device=DEV), None, T=1.0, num_steps=20, lmbd=1.0, d=d, sigma=sde.sigma)
-    opt = sb.FusedAdam(_groups(sde, solver.y0)[:3], lr=1e-3, eps=1e-8)
+    solver = sb.SOC_Solver(sde, torch.zeros(d, device=DEV), None, T=1.0, num_steps=50, lmbd=1.0, d=d, sigma=sde.sigma)
+    # main.py:188-230: lr 1e-4 for the control network, its own rates for the M-network and gamma
+    opt = sb.FusedAdam([{"params": list(sde.nabla_V.parameters())},
+                        {"params": list(sde.M.sigmoid_layers.parameters()), "lr": 1e-4},
+                        {"params": [sde.gamma], "lr": 1e-3}], lr=1e-4, eps=1e-8)
     trainer = sb.Trainer(solver, opt, "SOCM", 256, normalization_const=0.5)
     before = [p.detach().clone() for p in sde.nabla_V.parameters()]
     wms = []
