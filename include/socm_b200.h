@@ -232,6 +232,8 @@ int socm_ema_stats_f32(const socm_ema_tensor* tensors /* host array */, int32_t 
 #define SOCM_LOSS_FORCE_GENERIC 1u
 #define SOCM_LOSS_FORCE_FFMA 2u /* default net: fp32 FFMA tile kernel instead of the tcgen05 kernels */
 #define SOCM_LOSS_FORCE_TC 4u   /* default net: tcgen05 kernels even below SOCM_LOSS_TC_MIN_POINTS */
+#define SOCM_LOSS_F16 8u        /* default net, d <= 15: fp16-split tcgen05 engine, two CTAs per SM (csrc/loss_h.cu) */
+#define SOCM_LOSS_TF32 16u      /* default net: the 3xTF32 tcgen05 engine even where the fp16-split one is the default */
 #define SOCM_LOSS_TC_MIN_POINTS 65536 /* (K+1)*B from which the tcgen05 kernels are the default */
 int64_t socm_loss_workspace_bytes(const socm_unet* net, int32_t B, int32_t K);
 int64_t socm_unet_param_count(const socm_unet* net);

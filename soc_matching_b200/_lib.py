@@ -102,6 +102,8 @@ CONTROL_AFFINE, CONTROL_LOOKUP = 0, 1
 LOSS_FORCE_GENERIC = 1
 LOSS_FORCE_FFMA = 2
 LOSS_FORCE_TC = 4
+LOSS_F16 = 8
+LOSS_TF32 = 16
 
 _lib = None
 

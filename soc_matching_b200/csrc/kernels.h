@@ -25,5 +25,8 @@ namespace hx {
 bool rollout_h_supported(const socm_unet* net);
 int64_t rollout_h_workspace_bytes();
 int launch_rollout_h(const RolloutArgs& a, const socm_unet* net, void* workspace, cudaStream_t stream);
+// K3a on the same engine (loss_h.cu); K3b stays wgrad_tc.cu
+bool loss_h_supported(const socm_unet* net);
+int64_t loss_h_workspace_bytes(int B, int K);
 }  // namespace hx
 }  // namespace socm

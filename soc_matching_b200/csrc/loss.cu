@@ -40,6 +40,9 @@ int64_t loss_tile_workspace_bytes(int d, int B, int K);
 namespace tc {
 int launch_loss_tc(const LossArgs& a, const socm_unet* net, float* grad, void* workspace, cudaStream_t stream);
 }
+namespace hx {
+int launch_loss_h(const LossArgs& a, const socm_unet* net, float* grad, void* workspace, cudaStream_t stream);
+}
 
 }  // namespace socm
 
@@ -50,7 +53,8 @@ extern "C" int64_t socm_loss_workspace_bytes(const socm_unet* net, int32_t B, in
   if (!net) return -1;
   if (is_default_arch(net)) {
     const int64_t ffma = loss_tile_workspace_bytes(net->d, B, K);
-    const int64_t tcb = tc::loss_tc_supported(net) ? tc::loss_tc_workspace_bytes(net->d, B, K) : 0;
+    int64_t tcb = tc::loss_tc_supported(net) ? tc::loss_tc_workspace_bytes(net->d, B, K) : 0;
+    if (hx::loss_h_supported(net) && hx::loss_h_workspace_bytes(B, K) > tcb) tcb = hx::loss_h_workspace_bytes(B, K);
     return ffma > tcb ? ffma : tcb;
   }
   return 256;  // the generic kernel needs no workspace
@@ -87,6 +91,10 @@ extern "C" int socm_unet_loss_fwdbwd_f32(const socm_setting* st, const socm_unet
   // 3xTF32 forward differs from fp32 by ~2e-6, enough to flip a ReLU mask about once per 5e5
   // pre-activations, which is visible in the gradients of small problems)
   const bool want_tc = (flags & SOCM_LOSS_FORCE_TC) || (int64_t)(K + 1) * B >= SOCM_LOSS_TC_MIN_POINTS;
+  const bool want_f16 = (flags & SOCM_LOSS_F16) || f16_default() == 1;
+  if (hx::loss_h_supported(net) && want_tc && want_f16 &&
+      !(flags & (SOCM_LOSS_FORCE_GENERIC | SOCM_LOSS_FORCE_FFMA | SOCM_LOSS_TF32)))
+    return hx::launch_loss_h(a, net, grad, workspace, stream);
   if (tc::loss_tc_supported(net) && want_tc && !(flags & (SOCM_LOSS_FORCE_GENERIC | SOCM_LOSS_FORCE_FFMA)))
     return tc::launch_loss_tc(a, net, grad, workspace, stream);
   if (is_default_arch(net) && !(flags & SOCM_LOSS_FORCE_GENERIC)) return launch_loss_tile(a, net, grad, workspace, stream);

@@ -56,15 +56,7 @@ __device__ __forceinline__ void warp_max_to(uint32_t* slot, float v) {
 //       Philox normal z, at t in {0, T/3, 2T/3, T} -- the scale only has to be right within ~2^10 (head room) upwards
 //       and ~2^15 downwards (precision floor), see unet_h.cuh;
 //   loss mode: points of the stored trajectories, strided over all (K+1) B of them.
-struct CalibArgs {
-  const float* x0;        // rollout mode [B][d]
-  const float* step_tab;  // rollout mode [5][K] (row 4: t_k, row 0: dt_k)
-  const float* states;    // loss mode [K+1][B][d]
-  const float* ts;        // loss mode [K+1]
-  int B, K, n_samples;
-  float lmbd;
-  uint64_t seed;
-};
+constexpr int CALIB_BWD_FLOATS = 32 + H0 + 2 * H1 + H2;
 __global__ void __launch_bounds__(256) calib_h_kernel(socm_unet net, const float* __restrict__ wc, CalibArgs c,
                                                       uint32_t* __restrict__ mx) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -80,7 +72,7 @@ __global__ void __launch_bounds__(256) calib_h_kernel(socm_unet net, const float
     warp_max_to(mx + N_ACT + l, v);
     return;
   }
-  const int per_warp = generic::fwd_floats(d, H0, H1, H2);
+  const int per_warp = generic::fwd_floats(d, H0, H1, H2) + CALIB_BWD_FLOATS;
   generic::FwdBuf b = generic::carve_fwd(smem + (size_t)warp * per_warp, d, H0, H1, H2);
   for (int i = (blockIdx.x - 10) * 8 + warp; i < c.n_samples; i += (gridDim.x - 10) * 8) {
     if (c.states == nullptr) {
@@ -92,7 +84,9 @@ __global__ void __launch_bounds__(256) calib_h_kernel(socm_unet net, const float
         b.xin[0] = T * (float)v / 3.f;
         for (int blk = 0; blk * 4 < d; ++blk) {
           float z[4];
-          philox_normal4(c.seed ^ 0x5bd1e995u, (uint64_t)i, 0xffffu, (uint32_t)blk, z);
+          // fixed key: the calibration (hence the power-of-two scales, hence every rounding) must not depend on the
+          // call's noise seed, or replaying a run with its own noise injected would not be bit-identical
+          philox_normal4(0x5bd1e995c0ffee11ull, (uint64_t)i, 0xffffu, (uint32_t)blk, z);
           for (int j = 0; j < 4 && blk * 4 + j < d; ++j)
             b.xin[1 + blk * 4 + j] = __ldg(c.x0 + (size_t)m * d + blk * 4 + j) + r * z[j];
         }
@@ -118,23 +112,98 @@ __global__ void __launch_bounds__(256) calib_h_kernel(socm_unet net, const float
     warp_max_to(mx + A_O2, amax(b.o2, H1, false));
     warp_max_to(mx + A_Y1, amax(b.y1, H0, true));   // y1 holds the pre-ReLU values of up_1
     __syncwarp();
+    if (c.target != nullptr && c.states != nullptr) {
+      // backward gains: max |d_layer| for the row-normalised loss gradient dv / max|dv| at this point (loss_h.cu);
+      // dv ~ nabla_V - target up to a positive factor (sigma and the warm start only turn it slightly)
+      float* bw = smem + (size_t)warp * per_warp + generic::fwd_floats(d, H0, H1, H2);
+      float* d_y0 = bw;            // [d]
+      float* d_o1 = d_y0 + 32;     // [H0]
+      float* d_o2 = d_o1 + H0;     // [H1]
+      float* d_r2 = d_o2 + H1;     // [H1]
+      float* d_r3 = d_r2 + H1;     // [H2]
+      const size_t n_pts = (size_t)(c.K + 1) * c.B;
+      const size_t pt = (size_t)(((double)i + 0.5) / c.n_samples * (double)n_pts);
+      const int ti = (int)(pt / c.B), m = (int)(pt - (size_t)ti * c.B);
+      float dvm = 0.f;
+      for (int j = lane; j < d; j += 32) {
+        const float dv = b.o0[j] - __ldg(c.target + (size_t)m * c.ldt + (size_t)ti * d + j);
+        d_y0[j] = dv;
+        dvm = fmaxf(dvm, fabsf(dv));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dvm = fmaxf(dvm, __shfl_xor_sync(0xffffffffu, dvm, o));
+      if (dvm > 0.f) {
+        __syncwarp();
+        for (int j = lane; j < d; j += 32) d_y0[j] = b.y0[j] > 0.f ? d_y0[j] / dvm : 0.f;
+        __syncwarp();
+        generic::dense_t(net.w[8], d, H0, d_y0, d_o1, false, lane);
+        __syncwarp();
+        for (int k = lane; k < H0; k += 32) d_o1[k] = b.y1[k] > 0.f ? d_o1[k] : 0.f;   // d_y1
+        __syncwarp();
+        warp_max_to(mx + MX_B + B_DY1, amax(d_o1, H0, false));
+        generic::dense_t(net.w[7], H0, H1, d_o1, d_o2, false, lane);
+        __syncwarp();
+        warp_max_to(mx + MX_B + B_DO2, amax(d_o2, H1, false));
+        generic::dense_t(net.w[5], H1, H1, d_o2, d_r2, false, lane);
+        __syncwarp();
+        for (int k = lane; k < H1; k += 32) d_o2[k] = b.y2[k] > 0.f ? d_o2[k] : 0.f;   // d_y2
+        __syncwarp();
+        generic::dense_t(net.w[6], H1, H2, d_o2, d_r3, false, lane);
+        __syncwarp();
+        for (int k = lane; k < H2; k += 32) d_r3[k] = b.r3[k] > 0.f ? d_r3[k] : 0.f;   // d_z3
+        __syncwarp();
+        warp_max_to(mx + MX_B + B_DZ3, amax(d_r3, H2, false));
+        generic::dense_t(net.w[2], H2, H1, d_r3, d_r2, true, lane);
+        __syncwarp();
+        for (int k = lane; k < H1; k += 32) d_r2[k] = b.r2[k] > 0.f ? d_r2[k] : 0.f;   // d_z2
+        __syncwarp();
+        warp_max_to(mx + MX_B + B_DZ2, amax(d_r2, H1, false));
+      }
+      __syncwarp();
+    }
   }
 }
 
+// Scales (every thread recomputes them from the max buffer: a few dozen flops).  sw: weight scales (WScale), sa: forward
+// activation scales, sb: backward operand scales.  The row-normalised loss gradient has max |d_y0| in [1, 2).
+struct Scales {
+  float sa[N_ACT], sw[N_WSCALE], sb[N_BACT];
+};
+__device__ __forceinline__ Scales make_scales(const uint32_t* __restrict__ mx) {
+  Scales z;
+  for (int a = 0; a < N_ACT; ++a) z.sa[a] = pow2_scale(__uint_as_float(mx[a]), ACT_TARGET);
+  for (int l = 0; l < 10; ++l) z.sw[l] = pow2_scale(__uint_as_float(mx[N_ACT + l]), W_TARGET);
+  z.sb[B_DY0] = pow2_scale(2.f, ACT_TARGET);
+  for (int a = B_DY1; a < N_BACT; ++a) {
+    const float g = __uint_as_float(mx[MX_B + a]);
+    z.sb[a] = pow2_scale(g > 0.f ? 2.f * g : 2.f, ACT_TARGET);
+  }
+  // products that accumulate onto another product's accumulator arrive in its units; if that pushes the weight block
+  // out of the comfortable fp16 range, move the operand scale instead (it has 2^10 of head room and a 2^15 window)
+  auto matched = [&](float& s_op, float target_total, float wmax) {
+    float sw = target_total / s_op;
+    while (sw * wmax > 16384.f) { sw *= 0.5f; s_op *= 2.f; }
+    while (sw * wmax < 16.f && wmax > 0.f) { sw *= 2.f; s_op *= 0.5f; }
+    return sw;
+  };
+  z.sw[WS_D2T] = matched(z.sb[B_DZ3], z.sb[B_DO2] * z.sw[5], __uint_as_float(mx[N_ACT + 2]));
+  z.sw[WS_WCT] = matched(z.sb[B_DY0], z.sb[B_DZ2] * z.sw[1], __uint_as_float(mx[N_ACT + WC_LAYER]));
+  return z;
+}
+
 __global__ void pack_h_kernel(socm_unet net, const float* __restrict__ wc, const uint32_t* __restrict__ mx,
-                              unsigned char* __restrict__ tape, float* __restrict__ small) {
+                              unsigned char* __restrict__ tape, float* __restrict__ small, int with_bwd) {
   const int d = net.d;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   const Small so = small_layout();
-  float sa[N_ACT], sw[10];
-  for (int a = 0; a < N_ACT; ++a) sa[a] = pow2_scale(__uint_as_float(mx[a]), ACT_TARGET);
-  for (int l = 0; l < 10; ++l) sw[l] = pow2_scale(__uint_as_float(mx[N_ACT + l]), W_TARGET);
-  for (int it = 0; it < FWD_ITEMS; ++it) {
-    const PackItem pi = fwd_item(d, it);
+  const Scales z = make_scales(mx);
+  const int n_items = FWD_ITEMS + (with_bwd ? BWD_ITEMS : 0);
+  for (int it = 0; it < n_items; ++it) {
+    const PackItem pi = it < FWD_ITEMS ? fwd_item(d, it) : bwd_item(d, it - FWD_ITEMS);
     const SlotDesc sd = pi.sd;
     const float* W = sd.layer == WC_LAYER ? wc : net.w[sd.layer];
-    const float s = sw[sd.layer];
-    unsigned char* base = tape + (size_t)pi.slot * SLOT_BYTES + pi.byte_off;
+    const float s = z.sw[sd.sid >= 0 ? sd.sid : sd.layer];
+    unsigned char* base = tape + (size_t)(pi.slot + (it < FWD_ITEMS ? 0 : FWD_SLOTS)) * SLOT_BYTES + pi.byte_off;
     const int slab = (sd.slab_n ? sd.slab_n : sd.N) * sd.Kc * 2;
     for (int i = tid; i < sd.N * sd.Kc; i += nth) {
       const int n = i / sd.Kc, k = i - n * sd.Kc;
@@ -152,38 +221,48 @@ __global__ void pack_h_kernel(socm_unet net, const float* __restrict__ wc, const
   auto copy = [&](int off, const float* src, int n, float scale) {
     for (int i = tid; i < n; i += nth) small[off + i] = src[i] * scale;
   };
-  copy(so.b_d0, net.b[0], H0, sa[A_R1]);
-  copy(so.b_d1, net.b[1], H1, sa[A_R2]);
-  copy(so.b_d2, net.b[2], H2, sa[A_R3]);
-  copy(so.b_u2, net.b[6], H1, sa[A_O2]);
-  copy(so.b_r2, net.b[5], H1, sa[A_O2]);
-  copy(so.b_u1, net.b[7], H0, sa[A_Y1]);
+  copy(so.b_d0, net.b[0], H0, z.sa[A_R1]);
+  copy(so.b_d1, net.b[1], H1, z.sa[A_R2]);
+  copy(so.b_d2, net.b[2], H2, z.sa[A_R3]);
+  copy(so.b_u2, net.b[6], H1, z.sa[A_O2]);
+  copy(so.b_r2, net.b[5], H1, z.sa[A_O2]);
+  copy(so.b_u1, net.b[7], H0, z.sa[A_Y1]);
   for (int i = tid; i < KIN; i += nth) small[so.b_r0 + i] = i < d ? net.b[3][i] : 0.f;
   for (int i = tid; i < KIN * KIN; i += nth) {
     const int j = i / KIN, k = i - j * KIN;
     small[so.r0 + i] = (j < d && k <= d) ? net.w[3][(size_t)j * (d + 1) + k] : 0.f;
   }
   if (tid == 0) {
-    for (int a = 0; a < N_ACT; ++a) small[so.sa + a] = sa[a];
+    for (int a = 0; a < N_ACT; ++a) small[so.sa + a] = z.sa[a];
     for (int l = 0; l < 10; ++l) {
-      const float inv = 1.f / (sa[act_of_layer(l)] * sw[l]);
+      const float inv = 1.f / (z.sa[act_of_layer(l)] * z.sw[l]);
       small[so.inv + l] = inv;
-      small[so.invs + l] = act_out_of_layer(l) >= 0 ? inv * sa[act_out_of_layer(l)] : inv;
+      small[so.invs + l] = act_out_of_layer(l) >= 0 ? inv * z.sa[act_out_of_layer(l)] : inv;
+    }
+    for (int a = 0; a < N_BACT; ++a) small[so.sb + a] = z.sb[a];
+    // accumulator units of the five backward products: s_in * w
+    const float unit[N_BPROD] = {z.sb[B_DY0] * z.sw[8], z.sb[B_DY1] * z.sw[7], z.sb[B_DO2] * z.sw[6], z.sb[B_DO2] * z.sw[5],
+                                 z.sb[B_DZ2] * z.sw[1]};
+    const float s_out[N_BPROD] = {z.sb[B_DY1], z.sb[B_DO2], z.sb[B_DZ3], z.sb[B_DZ2], 1.f};
+    for (int q = 0; q < N_BPROD; ++q) {
+      small[so.bt + q] = 1.f / unit[q];
+      small[so.bf + q] = s_out[q] / unit[q];
     }
   }
 }
 
-int setup_h(const socm_unet* net, unsigned char* ws, const CalibArgs& c, cudaStream_t stream) {
+int setup_h(const socm_unet* net, unsigned char* ws, const CalibArgs& c, bool with_bwd, cudaStream_t stream) {
   float* small = small_ptr(ws);
   float* wc = wc_ptr(ws);
   uint32_t* mx = max_ptr(ws);
   SOCM_CUDA(cudaMemsetAsync(mx, 0, 64 * sizeof(uint32_t), stream));
   fold_h_kernel<<<NY, H0, 0, stream>>>(*net, wc, small);
   SOCM_LAUNCH_CHECK();
-  const size_t smem = 8 * (size_t)generic::fwd_floats(net->d, H0, H1, H2) * sizeof(float);
+  const size_t smem = 8 * (size_t)(generic::fwd_floats(net->d, H0, H1, H2) + CALIB_BWD_FLOATS) * sizeof(float);
+  SOCM_CUDA(cudaFuncSetAttribute(calib_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   calib_h_kernel<<<10 + (c.n_samples + 7) / 8, 256, smem, stream>>>(*net, wc, c, mx);
   SOCM_LAUNCH_CHECK();
-  pack_h_kernel<<<96, 256, 0, stream>>>(*net, wc, mx, ws, small);
+  pack_h_kernel<<<96, 256, 0, stream>>>(*net, wc, mx, ws, small, with_bwd ? 1 : 0);
   SOCM_LAUNCH_CHECK();
   return SOCM_OK;
 }
@@ -768,8 +847,7 @@ int launch_rollout_h(const RolloutArgs& a, const socm_unet* net, void* workspace
   c.n_samples = 256;
   c.step_tab = a.step_tab;
   c.lmbd = a.st.lmbd;
-  c.seed = a.seed;
-  if (int rc = setup_h(net, ws, c, stream)) return rc;
+  if (int rc = setup_h(net, ws, c, false, stream)) return rc;
   const int smem = rollout_h_smem_bytes();
   const int n_tiles = (a.B + TP - 1) / TP;
   const int max_ctas = 2 * sm_count();

@@ -67,6 +67,7 @@ struct SlotDesc {
   int transposed;  // 1: B[n][k] = W[k0 + k][n0 + n]  (dgrad tapes)
   int klim, nlim;  // zero padding beyond
   int slab_n, slab_row;  // block is rows [slab_row, slab_row + N) of a slab of slab_n rows (0: N)
+  int sid;               // weight-scale index (WScale); -1: the forward scale of `layer`
 };
 struct PackItem {
   int slot, byte_off;
@@ -75,27 +76,27 @@ struct PackItem {
 constexpr int NOLIM = 1 << 30;
 constexpr int FWD_ITEMS = 48;
 __host__ __device__ inline PackItem fwd_item(int d, int i) {
-  if (i < 2) return PackItem{FS_W0, i * PIECE_BYTES, SlotDesc{0, 32 * i, 32, 0, KIN, d + 1, 0, d + 1, NOLIM, 0, 0}};
+  if (i < 2) return PackItem{FS_W0, i * PIECE_BYTES, SlotDesc{0, 32 * i, 32, 0, KIN, d + 1, 0, d + 1, NOLIM, 0, 0, -1}};
   i -= 2;
-  if (i < 8) return PackItem{FS_D1 + i, 0, SlotDesc{1, 0, H1, 32 * i, 32, H0, 0, NOLIM, NOLIM, H1 + NY, 0}};
+  if (i < 8) return PackItem{FS_D1 + i, 0, SlotDesc{1, 0, H1, 32 * i, 32, H0, 0, NOLIM, NOLIM, H1 + NY, 0, -1}};
   i -= 8;
-  if (i < 8) return PackItem{FS_D1 + i, 0, SlotDesc{WC_LAYER, 0, NY, 32 * i, 32, H0, 0, NOLIM, d, H1 + NY, H1}};
+  if (i < 8) return PackItem{FS_D1 + i, 0, SlotDesc{WC_LAYER, 0, NY, 32 * i, 32, H0, 0, NOLIM, d, H1 + NY, H1, -1}};
   i -= 8;
-  if (i < 6) return PackItem{FS_D1 + i, D1_MAIN, SlotDesc{0, 32 * (i + 2), 32, 0, KIN, d + 1, 0, d + 1, NOLIM, 0, 0}};
+  if (i < 6) return PackItem{FS_D1 + i, D1_MAIN, SlotDesc{0, 32 * (i + 2), 32, 0, KIN, d + 1, 0, d + 1, NOLIM, 0, 0, -1}};
   i -= 6;
-  if (i < 2) return PackItem{FS_D2 + i, 0, SlotDesc{2, 0, H2, 64 * i, 64, H1, 0, NOLIM, NOLIM, 0, 0}};
+  if (i < 2) return PackItem{FS_D2 + i, 0, SlotDesc{2, 0, H2, 64 * i, 64, H1, 0, NOLIM, NOLIM, 0, 0, -1}};
   i -= 2;
-  if (i < 2) return PackItem{FS_R2B + i, 0, SlotDesc{5, 64, 64, 64 * i, 64, H1, 0, NOLIM, NOLIM, 0, 0}};
+  if (i < 2) return PackItem{FS_R2B + i, 0, SlotDesc{5, 64, 64, 64 * i, 64, H1, 0, NOLIM, NOLIM, 0, 0, -1}};
   i -= 2;
-  if (i < 2) return PackItem{FS_R2A + i, 0, SlotDesc{5, 0, 64, 64 * i, 64, H1, 0, NOLIM, NOLIM, 0, 0}};
+  if (i < 2) return PackItem{FS_R2A + i, 0, SlotDesc{5, 0, 64, 64 * i, 64, H1, 0, NOLIM, NOLIM, 0, 0, -1}};
   i -= 2;
-  if (i < 2) return PackItem{FS_U2 + i, 0, SlotDesc{6, 0, H1, 32 * i, 32, H2, 0, NOLIM, NOLIM, 0, 0}};
+  if (i < 2) return PackItem{FS_U2 + i, 0, SlotDesc{6, 0, H1, 32 * i, 32, H2, 0, NOLIM, NOLIM, 0, 0, -1}};
   i -= 2;
-  if (i < 8) return PackItem{FS_U1 + i, 0, SlotDesc{7, 32 * i, 32, 0, H1, H1, 0, NOLIM, NOLIM, 0, 0}};
+  if (i < 8) return PackItem{FS_U1 + i, 0, SlotDesc{7, 32 * i, 32, 0, H1, H1, 0, NOLIM, NOLIM, 0, 0, -1}};
   i -= 8;
-  if (i < 6) return PackItem{FS_U1 + 2 + i, U1_MAIN, SlotDesc{8, 0, NY, 32 * i, 32, H0, 0, NOLIM, d, 0, 0}};
+  if (i < 6) return PackItem{FS_U1 + 2 + i, U1_MAIN, SlotDesc{8, 0, NY, 32 * i, 32, H0, 0, NOLIM, d, 0, 0, -1}};
   i -= 6;
-  return PackItem{FS_U0, i * PIECE_BYTES, SlotDesc{8, 0, NY, 32 * (6 + i), 32, H0, 0, NOLIM, d, 0, 0}};
+  return PackItem{FS_U0, i * PIECE_BYTES, SlotDesc{8, 0, NY, 32 * (6 + i), 32, H0, 0, NOLIM, d, 0, 0, -1}};
 }
 __host__ __device__ inline uint32_t fwd_slot_bytes(int s) {
   if (s == FS_W0) return 2 * PIECE_BYTES;
@@ -104,6 +105,44 @@ __host__ __device__ inline uint32_t fwd_slot_bytes(int s) {
   if (s < FS_U1 + 2) return (uint32_t)U1_MAIN;
   if (s < FS_U0) return (uint32_t)(U1_MAIN + PIECE_BYTES);
   return (uint32_t)(2 * PIECE_BYTES);
+}
+
+// backward (dgrad) tape, W^T blocks: slot 0: up_0^T pieces 0,1 | 1..8: up_1^T chunk c + up_0^T piece c+2 | 9,10: up_2^T
+// (two K = 32 blocks per slot) | 11,12: res_2^T b | 13,14: res_2^T a | 15: down_2^T a | 16: down_2^T b |
+// 17..24: down_1^T piece q + Wc^T piece q
+constexpr int BWD_SLOTS = 25;
+enum BwdSlot { BS_U0T = 0, BS_U1T = 1, BS_U2T = 9, BS_R2TB = 11, BS_R2TA = 13, BS_D2TA = 15, BS_D2TB = 16, BS_D1T = 17 };
+// weight scales: 0..9 forward (layer index, WC_LAYER = 9); backward blocks reuse the forward scale of their matrix except
+// the two products that ACCUMULATE ONTO another product's accumulator and must arrive in its units:
+//   down_2^T onto res_2^T (d_r2):  s_dz3 w_d2T = s_do2 w_r2     |     Wc^T onto down_1^T (d_r1):  s_dy0 w_wcT = s_dz2 w_d1
+enum WScale { WS_D2T = 10, WS_WCT = 11, N_WSCALE = 12 };
+constexpr int BWD_ITEMS = 44;
+__host__ __device__ inline PackItem bwd_item(int d, int i) {
+  if (i < 2) return PackItem{BS_U0T, i * PIECE_BYTES, SlotDesc{8, 32 * i, 32, 0, KIN, H0, 1, d, NOLIM, 0, 0, -1}};
+  i -= 2;
+  if (i < 8) return PackItem{BS_U1T + i, 0, SlotDesc{7, 0, H1, 32 * i, 32, H1, 1, NOLIM, NOLIM, 0, 0, -1}};
+  i -= 8;
+  if (i < 6) return PackItem{BS_U1T + i, 16384, SlotDesc{8, 32 * (i + 2), 32, 0, KIN, H0, 1, d, NOLIM, 0, 0, -1}};
+  i -= 6;
+  if (i < 4) return PackItem{BS_U2T + i / 2, (i % 2) * 8192, SlotDesc{6, 0, H2, 32 * i, 32, H2, 1, NOLIM, NOLIM, 0, 0, -1}};
+  i -= 4;
+  if (i < 2) return PackItem{BS_R2TB + i, 0, SlotDesc{5, 64, 64, 64 * i, 64, H1, 1, NOLIM, NOLIM, 0, 0, -1}};
+  i -= 2;
+  if (i < 2) return PackItem{BS_R2TA + i, 0, SlotDesc{5, 0, 64, 64 * i, 64, H1, 1, NOLIM, NOLIM, 0, 0, -1}};
+  i -= 2;
+  if (i < 2) return PackItem{BS_D2TA, i * 8192, SlotDesc{2, 0, 64, 32 * i, 32, H1, 1, NOLIM, NOLIM, 0, 0, WS_D2T}};
+  i -= 2;
+  if (i < 2) return PackItem{BS_D2TB, i * 8192, SlotDesc{2, 64, 64, 32 * i, 32, H1, 1, NOLIM, NOLIM, 0, 0, WS_D2T}};
+  i -= 2;
+  if (i < 8) return PackItem{BS_D1T + i, 0, SlotDesc{1, 32 * i, 32, 0, H1, H0, 1, NOLIM, NOLIM, 0, 0, -1}};
+  i -= 8;
+  return PackItem{BS_D1T + i, U1_MAIN, SlotDesc{WC_LAYER, 32 * i, 32, 0, KIN, H0, 1, d, NOLIM, 0, 0, WS_WCT}};
+}
+__host__ __device__ inline uint32_t bwd_slot_bytes(int s) {
+  if (s == BS_U0T) return 2 * PIECE_BYTES;
+  if (s < BS_U2T) return (uint32_t)(16384 + (s - BS_U1T < 6 ? PIECE_BYTES : 0));
+  if (s < BS_D1T) return 16384u;
+  return (uint32_t)(U1_MAIN + PIECE_BYTES);
 }
 
 // ---------------------------------------------------------------- small block (floats, read from shared memory)
@@ -117,8 +156,15 @@ struct Small {
   // (r1, r2, r3, o2, o2, y1), and `invs` = inv * that scale: relu(acc inv + b) s = relu(acc (inv s) + b s) for s > 0,
   // which saves one multiply per element in the epilogue.
   int invs;  // [10]
+  // backward (dgrad chain on row-normalised gradients, see loss_h.cu): operand scales and the accumulator -> operand /
+  // accumulator -> true-value factors of the five products
+  int sb;    // [N_BACT]  scales of the backward operands d_y0, d_y1, d_o2 (= d_y2), d_z3, d_z2
+  int bf;    // [N_BPROD] acc -> next operand:   s_out / (s_in w)
+  int bt;    // [N_BPROD] acc -> normalised true value: 1 / (s_in w)
   int total;
 };
+enum BAct { B_DY0 = 0, B_DY1, B_DO2, B_DZ3, B_DZ2, N_BACT };
+enum BProd { P_U0T = 0, P_U1T, P_U2T, P_R2T, P_D1T, N_BPROD };   // d_o1, d_o2, d_r3, d_r2 (res_2^T + down_2^T), d_r1
 __host__ __device__ inline Small small_layout() {
   Small o;
   int p = 0;
@@ -134,6 +180,9 @@ __host__ __device__ inline Small small_layout() {
   o.sa = p; p += 8;
   o.inv = p; p += 12;
   o.invs = p; p += 12;
+  o.sb = p; p += 8;
+  o.bf = p; p += 8;
+  o.bt = p; p += 8;
   o.total = ((p + 3) / 4) * 4;
   return o;
 }
@@ -164,14 +213,18 @@ __host__ __device__ inline int act_out_of_layer(int l) {
   }
 }
 // workspace: [tape FWD_SLOTS x SLOT_BYTES][small][Wc 16 x 256 floats][max buffer: N_ACT + 10 uint32]
+// workspace: [forward tape][backward tape][small][Wc 16 x 256 floats][max buffer 64 uint32]  (the backward tape is always
+// reserved; the rollout does not fill it)
 constexpr int WC_FLOATS = NY * H0;
-__host__ __device__ inline int64_t tape_bytes() { return (int64_t)FWD_SLOTS * SLOT_BYTES; }
+__host__ __device__ inline int64_t tape_bytes() { return (int64_t)(FWD_SLOTS + BWD_SLOTS) * SLOT_BYTES; }
 __host__ __device__ inline int64_t workspace_bytes() {
   return tape_bytes() + (int64_t)small_layout().total * 4 + (int64_t)WC_FLOATS * 4 + 64 * 4;
 }
 __host__ __device__ inline float* small_ptr(unsigned char* ws) { return reinterpret_cast<float*>(ws + tape_bytes()); }
 __host__ __device__ inline float* wc_ptr(unsigned char* ws) { return small_ptr(ws) + small_layout().total; }
 __host__ __device__ inline uint32_t* max_ptr(unsigned char* ws) { return reinterpret_cast<uint32_t*>(wc_ptr(ws) + WC_FLOATS); }
+// max buffer slots: [0, N_ACT) forward activations, [N_ACT, N_ACT + 10) weights, [MX_B, MX_B + N_BACT) backward gains
+constexpr int MX_B = 24;
 
 // power-of-two scale that maps `mx` into [target / 2, target)
 __host__ __device__ inline float pow2_scale(float mx, float target) {
@@ -196,6 +249,21 @@ __device__ __forceinline__ void issue_ts(uint32_t d_tmem, uint32_t a_tmem, uint3
     umma::mma_ts_f16(d_tmem, a_tmem + 16 * ks, bh, id, (fresh && ks == 0) ? 0u : 1u);
     umma::mma_ts_f16(d_tmem, a_tmem + 16 * ks + 8, bh, id, 1u);
     umma::mma_ts_f16(d_tmem, a_tmem + 16 * ks, bl, id, 1u);
+  }
+}
+// the same with the A operand in two column ranges: k-steps [0, KS/2) at a0, [KS/2, KS) at a1
+template <int N, int KS>
+__device__ __forceinline__ void issue_ts2(uint32_t d_tmem, uint32_t a0, uint32_t a1, uint32_t b_smem, uint32_t kc, bool fresh) {
+  constexpr uint32_t id = umma::idesc_f16(TP, N);
+  const uint32_t slab = (uint32_t)N * kc * 2, sbo = kc * 16;
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const uint64_t bh = umma::smem_desc(b_smem + ks * W_KSTEP, W_LBO, sbo);
+    const uint64_t bl = umma::smem_desc(b_smem + slab + ks * W_KSTEP, W_LBO, sbo);
+    const uint32_t a = ks < KS / 2 ? a0 + 16 * ks : a1 + 16 * (ks - KS / 2);
+    umma::mma_ts_f16(d_tmem, a, bh, id, (fresh && ks == 0) ? 0u : 1u);
+    umma::mma_ts_f16(d_tmem, a + 8, bh, id, 1u);
+    umma::mma_ts_f16(d_tmem, a, bl, id, 1u);
   }
 }
 // A operand in shared memory (chunk layout; lo part at a_smem + a_lo_off); the block has `slab_rows` rows per slab
@@ -245,6 +313,20 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar) {
   if ((threadIdx.x & 31) == 0) umma::mbar_arrive(bar);
 }
 __device__ __forceinline__ void e_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the 8 epilogue warps
+
+// ---------------------------------------------------------------- per-call setup (rollout_h.cu)
+// Calibration sample points: rollout mode (states == nullptr): the first paths' x0 spread by Philox noise at four times;
+// loss mode: points of the stored trajectories (+ the loss gradient at them for the backward gains).
+struct CalibArgs {
+  const float* x0;        // rollout mode [B][d]
+  const float* step_tab;  // rollout mode [5][K] (row 4: t_k, row 0: dt_k)
+  const float* states;    // loss mode [K+1][B][d]
+  const float* ts;        // loss mode [K+1]
+  const float* target;    // loss mode [B][ldt]
+  int B, K, ldt, n_samples;
+  float lmbd;
+};
+int setup_h(const socm_unet* net, unsigned char* ws, const CalibArgs& c, bool with_bwd, cudaStream_t stream);
 
 }  // namespace hx
 }  // namespace socm

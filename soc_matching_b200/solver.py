@@ -297,7 +297,8 @@ class SOC_Solver(nn.Module):
                         _lib.ptr(G), _lib.ptr(grad_flat), _lib.ptr(loss_sum), _lib.ptr(loss_ws),
                         (_lib.LOSS_FORCE_GENERIC if self.force_generic else 0)
                         | (_lib.LOSS_FORCE_FFMA if self.force_ffma else 0)
-                        | (_lib.LOSS_FORCE_TC if self.force_tc else 0), stream)
+                        | (_lib.LOSS_FORCE_TC if self.force_tc else 0)
+                        | {None: 0, "f16": _lib.LOSS_F16, "tf32": _lib.LOSS_TF32}[simulate.ENGINE], stream)
             if L is not None:
                 if simt_target:                                # fp32 SIMT GEMM
                     self._timed("target_bwd", 1, lib.socm_target_gemm_bwd_f32, _lib.ptr(G), _lib.ptr(R), nb, K, d, ldr,
@@ -436,7 +437,8 @@ class SOC_Solver(nn.Module):
                     _lib.ptr(loss_sum), _lib.ptr(loss_ws),
                     (_lib.LOSS_FORCE_GENERIC if self.force_generic else 0)
                     | (_lib.LOSS_FORCE_FFMA if self.force_ffma else 0)
-                    | (_lib.LOSS_FORCE_TC if self.force_tc else 0), _lib.stream_ptr())
+                    | (_lib.LOSS_FORCE_TC if self.force_tc else 0)
+                        | {None: 0, "f16": _lib.LOSS_F16, "tf32": _lib.LOSS_TF32}[simulate.ENGINE], _lib.stream_ptr())
         del keep
         objective = _FusedObjective.apply(obj.detach().float(), None, None, grad_flat, *uparams)
         if algorithm == "moment":                      # d/d y0 through the torch-side functional
