@@ -91,7 +91,8 @@ extern "C" int socm_unet_loss_fwdbwd_f32(const socm_setting* st, const socm_unet
   // 3xTF32 forward differs from fp32 by ~2e-6, enough to flip a ReLU mask about once per 5e5
   // pre-activations, which is visible in the gradients of small problems)
   const bool want_tc = (flags & SOCM_LOSS_FORCE_TC) || (int64_t)(K + 1) * B >= SOCM_LOSS_TC_MIN_POINTS;
-  const bool want_f16 = (flags & SOCM_LOSS_F16) || f16_default() == 1;
+  // fp16-split engine (two CTAs per SM, csrc/loss_h.cu) wherever it applies; SOCM_F16=0 / SOCM_LOSS_TF32 select the 3xTF32 one
+  const bool want_f16 = (flags & SOCM_LOSS_F16) || f16_default() != 0;
   if (hx::loss_h_supported(net) && want_tc && want_f16 &&
       !(flags & (SOCM_LOSS_FORCE_GENERIC | SOCM_LOSS_FORCE_FFMA | SOCM_LOSS_TF32)))
     return hx::launch_loss_h(a, net, grad, workspace, stream);

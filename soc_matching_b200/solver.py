@@ -116,12 +116,18 @@ class SOC_Solver(nn.Module):
         tc = (not self.force_ffma) and udesc.d <= 23 and (self.force_tc or (K + 1) * nb >= 65536)
         if not tc:
             return 3
-        # tcgen05: fold + pack, (K3a + K3b) per sub-launch, fold_finish
         n_tiles = (K + 1) * ((nb + 127) // 128)
         import ctypes
+        import os
         sms = ctypes.c_int(0)
         _lib.check(_lib.load().socm_device_info(ctypes.byref(sms), None))
-        sub = (8192 // max(int(sms.value), 1)) * max(int(sms.value), 1)   # csrc/loss_tc.cu: sub_tiles_max()
+        n_sm = max(int(sms.value), 1)
+        f16 = udesc.d <= 15 and simulate.ENGINE != "tf32" and os.environ.get("SOCM_F16", "1") != "0"
+        if f16:   # csrc/loss_h.cu: fold + calibration + pack, (K3a + K3b) per sub-launch of 8192 // (2 SMs) * (2 SMs) tiles, fold_finish
+            sub = (8192 // (2 * n_sm)) * (2 * n_sm)
+            return 4 + 2 * ((n_tiles + sub - 1) // sub)
+        # csrc/loss_tc.cu: fold + pack, (K3a + K3b) per sub-launch, fold_finish
+        sub = (8192 // n_sm) * n_sm
         return 3 + 2 * ((n_tiles + sub - 1) // sub)
 
     def _grid(self):

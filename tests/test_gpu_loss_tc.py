@@ -14,6 +14,18 @@ from helpers import gpu_kink_free_noise, make_product_sde, orc, random_setting, 
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
+
+
+@pytest.fixture(params=["f16", "tf32"], autouse=True)
+def engine(request):
+    """Every test of this file runs on both tensor-core engines: the fp16-split one with two CTAs per SM
+    (csrc/unet_h.cuh, the default for d <= 15) and the 3xTF32 one (csrc/unet_tc.cuh)."""
+    from soc_matching_b200 import simulate
+    simulate.ENGINE = request.param
+    yield request.param
+    simulate.ENGINE = None
+
+
 NAMES = ["down_0", "down_1", "down_2", "res_0", "res_1", "res_2", "up_2", "up_1", "up_0"]
 
 
@@ -29,7 +41,7 @@ def unet64(P, tx):
 
 
 @pytest.mark.parametrize("d,K,B", [(10, 40, 300), (1, 30, 129), (20, 9, 200)])
-def test_k3_tc_matches_fp64_autograd_away_from_kinks(d, K, B):
+def test_k3_tc_matches_fp64_autograd_away_from_kinks(d, K, B, engine):
     from soc_matching_b200 import _lib, networks
     lib = _lib.load()
     p = {k: v.to(DEV) for k, v in seeded_unet(d, [256, 128, 64], 31 + d).items()}
@@ -63,7 +75,9 @@ def test_k3_tc_matches_fp64_autograd_away_from_kinks(d, K, B):
     scale = 1.0 / ((K + 1) * B)
     _lib.check(lib.socm_unet_loss_fwdbwd_f32(st, udesc, None, ts.data_ptr(), states.data_ptr(), target.data_ptr(),
                                              ldt, w.data_ptr(), None, scale, B, K, G.data_ptr(), grad.data_ptr(),
-                                             loss.data_ptr(), ws.data_ptr(), _lib.LOSS_FORCE_TC, _lib.stream_ptr()))
+                                             loss.data_ptr(), ws.data_ptr(),
+                                             _lib.LOSS_FORCE_TC | (_lib.LOSS_F16 if engine == "f16" else _lib.LOSS_TF32),
+                                             _lib.stream_ptr()))
     torch.cuda.synchronize()
     tx = torch.cat([ts.reshape(-1, 1, 1).expand(K + 1, B, 1), states], -1).double()
     out, _ = unet64(P, tx)
@@ -271,7 +285,7 @@ def test_full_chunk_tc_iteration_agrees_with_fp32_ffma():
         assert errs[n] <= 1e-4, (n, errs[n])
 
 
-def test_full_chunk_k3_tc_against_fp64_autograd():
+def test_full_chunk_k3_tc_against_fp64_autograd(engine):
     """K3 on the tensor cores against torch fp64 autograd over all 15.2 M points of a real bench chunk (states of a
     tcgen05 rollout, double_well d=10, K=200, B=75 776; a well-conditioned random target): every gradient tensor
     within 1e-4 (measured 2e-5..4.5e-5; the fp32 FFMA kernel: 1e-7..1.3e-5), loss 1e-6.  This is the error of the
@@ -303,7 +317,9 @@ def test_full_chunk_k3_tc_against_fp64_autograd():
     loss = torch.zeros(1, device=DEV, dtype=torch.float64)
     _lib.check(lib.socm_unet_loss_fwdbwd_f32(st, udesc, None, ts.data_ptr(), states.data_ptr(), target.data_ptr(), ldt,
                                              w.data_ptr(), None, scale, B, K, G.data_ptr(), grad.data_ptr(),
-                                             loss.data_ptr(), ws.data_ptr(), _lib.LOSS_FORCE_TC, _lib.stream_ptr()))
+                                             loss.data_ptr(), ws.data_ptr(),
+                                             _lib.LOSS_FORCE_TC | (_lib.LOSS_F16 if engine == "f16" else _lib.LOSS_TF32),
+                                             _lib.stream_ptr()))
     torch.cuda.synchronize()
     P = {n + sfx: getattr(getattr(unet, n)[0], sfx[1:]).detach().double().requires_grad_(True)
          for n in NAMES for sfx in (".weight", ".bias")}

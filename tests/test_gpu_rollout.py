@@ -54,7 +54,7 @@ CASES = [  # kind, d, K, B, lmbd, dense sigma
 
 
 @pytest.mark.parametrize("kind,d,K,B,lmbd,dense", CASES)
-@pytest.mark.parametrize("kernel", ["tc", "ffma", "generic"])
+@pytest.mark.parametrize("kernel", ["tc", "f16", "ffma", "generic"])
 def test_rollout_default_width_matches_oracle(kind, d, K, B, lmbd, dense, kernel):
     import soc_matching_b200 as sb
     st = random_setting(kind, d, seed=d * 7 + K, lmbd=lmbd, dense_sigma=dense)
@@ -69,8 +69,15 @@ def test_rollout_default_width_matches_oracle(kind, d, K, B, lmbd, dense, kernel
     torch.set_num_threads(8)
     want = orc.rollout(st, unet, x0.repeat(B, 1), ts, noises=noises)
     sde = make_product_sde(st, unet, mnet, gam, hd, hm, DEV, stopping=(kind == "molecular_dynamics"))
-    got = sb.stochastic_trajectories(sde, x0.to(DEV).repeat(B, 1), ts.to(DEV), lmbd, noises=noises.to(DEV),
-                                     force_generic=(kernel == "generic"), force_ffma=(kernel == "ffma"))
+    from soc_matching_b200 import simulate
+    if kernel == "f16" and d > 15:
+        pytest.skip("the fp16-split engine covers d <= 15")
+    simulate.ENGINE = {"tc": "tf32", "f16": "f16"}.get(kernel)
+    try:
+        got = sb.stochastic_trajectories(sde, x0.to(DEV).repeat(B, 1), ts.to(DEV), lmbd, noises=noises.to(DEV),
+                                         force_generic=(kernel == "generic"), force_ffma=(kernel == "ffma"))
+    finally:
+        simulate.ENGINE = None
     if kind == "molecular_dynamics":
         assert (want[2][-1] == 0).sum() > 5, "test needs stopped paths"
     compare_rollout(got, want)
@@ -159,14 +166,21 @@ def test_full_size_rollout_properties():
     sde = _dw_sde()
     K, B = 200, 1 << 20
     ts = torch.linspace(0, 1.0, K + 1, device=DEV)
-    big = simulate.rollout(sde, torch.zeros(B, 10, device=DEV), ts, 1.0, seed=2024)
-    assert torch.isfinite(big.lw).all() and torch.isfinite(big.states[-1]).all()
-    for m0 in (0, 12345 * 64, B - 64):
-        small = simulate.rollout(sde, torch.zeros(64, 10, device=DEV), ts, 1.0, seed=2024, path_offset=m0)
-        assert torch.equal(small.states, big.states[:, m0:m0 + 64])
-        assert torch.equal(small.lw, big.lw[:, m0:m0 + 64])
-    del big
-    torch.cuda.empty_cache()
+    # the default dispatch picks the tensor-core engine by batch size (fp16-split with two CTAs per SM for many
+    # tiles, 3xTF32 for a single wave): bit-identity across batch sizes holds per engine, so both are pinned here
+    for engine in ("f16", "tf32"):
+        simulate.ENGINE = engine
+        try:
+            big = simulate.rollout(sde, torch.zeros(B, 10, device=DEV), ts, 1.0, seed=2024)
+            assert torch.isfinite(big.lw).all() and torch.isfinite(big.states[-1]).all()
+            for m0 in (0, 12345 * 64, B - 64):
+                small = simulate.rollout(sde, torch.zeros(64, 10, device=DEV), ts, 1.0, seed=2024, path_offset=m0)
+                assert torch.equal(small.states, big.states[:, m0:m0 + 64]), (engine, m0)
+                assert torch.equal(small.lw, big.lw[:, m0:m0 + 64]), (engine, m0)
+        finally:
+            simulate.ENGINE = None
+        del big
+        torch.cuda.empty_cache()
 
 
 def test_full_chunk_tc_rollout_agrees_with_fp32_ffma():
@@ -180,10 +194,15 @@ def test_full_chunk_tc_rollout_agrees_with_fp32_ffma():
     K, B = 200, 75776
     ts = torch.linspace(0, 1.0, K + 1, device=DEV)
     x0 = torch.zeros(B, 10, device=DEV)
-    a = simulate.rollout(sde, x0, ts, 1.0, seed=7)
     b = simulate.rollout(sde, x0, ts, 1.0, seed=7, force_ffma=True)
-    assert torch.equal(a.noises, b.noises)
-    assert torch.equal(a.stop, b.stop)
-    assert rel_l2(a.states, b.states) <= 1e-5, rel_l2(a.states, b.states)
-    assert rel_l2(a.controls, b.controls) <= 1e-5, rel_l2(a.controls, b.controls)
-    assert rel_l2(a.lw, b.lw) <= 1e-5, rel_l2(a.lw, b.lw)
+    for engine in ("f16", "tf32"):
+        simulate.ENGINE = engine
+        try:
+            a = simulate.rollout(sde, x0, ts, 1.0, seed=7)
+        finally:
+            simulate.ENGINE = None
+        assert torch.equal(a.noises, b.noises)
+        assert torch.equal(a.stop, b.stop)
+        assert rel_l2(a.states, b.states) <= 1e-5, (engine, rel_l2(a.states, b.states))
+        assert rel_l2(a.controls, b.controls) <= 1e-5, (engine, rel_l2(a.controls, b.controls))
+        assert rel_l2(a.lw, b.lw) <= 1e-5, (engine, rel_l2(a.lw, b.lw))
