@@ -1,14 +1,14 @@
 // loss_h.cu -- K3a on the fp16-split tcgen05 engine (unet_h.cuh), two CTAs per SM: UNet forward at 128 trajectory points,
 // weighted loss and the whole dgrad chain.  Replaces method.py:272-287 (nabla_V at all points), 692-720 (loss) and the
-// activation-gradient half of loss.backward() (main.py:323); the weight gradients are K3b (wgrad_tc.cu), which reads the
-// operands this kernel leaves in the scratch layout of loss_tc.cuh (fp32, unchanged).
+// activation-gradient half of loss.backward() (main.py:323); the weight gradients are K3b (wgrad_h.cu), which reads the
+// operands this kernel leaves in the scratch: the geometry of loss_tc.cuh, but every feature row holds the 32 points of
+// its tile quarter as [fp16 hi x 32 | fp16 lo x 32] of the operand-scaled value -- the hi / lo pairs this kernel computes
+// for its own MMAs anyway, so the scratch costs two 2-byte stores per value and K3b needs no split pass.
 //
 // A tile is 128 consecutive paths at one grid time t_i.  Forward = the rollout's forward (rollout_h.cu) from the stored
-// state, ReLU masks kept in registers.  Backward = its mirror image on the transposed weight tape, on ROW-NORMALISED
-// gradients: the loss gradient of point p is scaled by rho_p = 2^-e (e = exponent of max_j |d loss / d nabla_V_j|), so that
-// every row enters the fp16 operands with its largest entry in [1, 2) however small the importance weight of its path
-// is (the chain is linear per row: exact).  Per-layer operand scales come from the calibration pass (rollout_h.cu),
-// the scratch receives true values (x 1 / rho_p).
+// state, ReLU masks kept in registers.  Backward = its mirror image on the transposed weight tape.  The loss gradient
+// d loss / d nabla_V carries ONE global power-of-two scale (from the exact max |w| and the sampled max |nabla_V - target|,
+// rollout_h.cu: make_scales), every later gradient tensor a per-layer one from the calibration pass.
 //   d_o1 = W_u0^T d_y0 (8 pieces)  ->  d_y1 = m_y1 . d_o1 (chunks)  ->  d_o2 = W_u1^T d_y1
 //   d_r3 = W_u2^T (m_y2 . d_o2),  d_z3 = m_r3 . d_r3
 //   d_r2 = W_r2^T d_o2 + W_d2^T d_z3,  d_z2 = m_r2 . d_r2
@@ -39,8 +39,7 @@ namespace k3 {
 constexpr int SM_RING = 0;
 constexpr int SM_CHUNK = SM_RING + NSTAGE * SLOT_BYTES;
 constexpr int SM_XIN = SM_CHUNK + 2 * CHUNK_BYTES;   // [t,x] operand (forward) / d_y0 operand (backward)
-constexpr int SM_IRHO = SM_XIN + 2 * XIN_HALF;       // 1 / rho_p of the tile's points (owners -> helpers)
-constexpr int SM_SMALL = SM_IRHO + TP * 4;
+constexpr int SM_SMALL = SM_XIN + 2 * XIN_HALF;
 enum Bar {
   W_FULL = 0, W_EMPTY = W_FULL + NSTAGE, CH_FULL = W_EMPTY + NSTAGE, CH_EMPTY = CH_FULL + 2, PC_FULL = CH_EMPTY + 2,
   PC_EMPTY = PC_FULL + 2,
@@ -56,19 +55,31 @@ constexpr uint32_t C_DR3 = 0, C_DR2A = 0, C_DR2B = 192, C_BPC = 64;   // backwar
 
 __host__ __device__ inline int loss_h_smem_bytes() { return k3::SM_SMALL + small_layout().total * 4 + k3::N_BARS * 8 + 16; }
 
-// Scratch stores (layout of loss_tc.cuh): thread <-> point r of the quarter; `ro` = the eight lane-dependent chunk
-// offsets ((r >> 2) ^ k) * 16 + (r & 3) * 4, k = f & 7.
+// Scratch stores: thread <-> point r of the quarter.  Row of feature f (128 bytes, 16-byte chunks XOR-permuted by
+// k = f & 7): the hi half of point r sits in logical chunk r >> 3, the lo half in chunk 4 + (r >> 3), at 2 (r & 7)
+// inside the chunk.  `ro.o[k]` = byte offset of the hi half inside the row; the lo half is that offset ^ 64.
 struct RowOff {
   int o[8];
   __device__ __forceinline__ explicit RowOff(int r) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = ((((r >> 2) ^ k) & 7) << 4) + (r & 3) * 4;
+    for (int k = 0; k < 8; ++k) o[k] = ((((r >> 3) ^ k) & 7) << 4) + 2 * (r & 7);
   }
 };
-// features [f0, f0 + 16) of feature block `blk`, values v[j] * mul (one coalesced 128-byte line per warp-wide store)
-__device__ __forceinline__ void store_fb16(unsigned char* blk, const RowOff& ro, int f0, const float* v, float mul) {
+__device__ __forceinline__ void st_half(unsigned char* p, uint32_t v) {
+  __stcs(reinterpret_cast<unsigned short*>(p), (unsigned short)v);
+}
+// features [f0, f0 + 16) of feature block `blk` from the packed pairs hi[i] / lo[i] = features (f0 + 2 i, f0 + 2 i + 1)
+// (f0 a multiple of 16: the chunk permutation index of feature f0 + j is j & 7)
+__device__ __forceinline__ void store_fb16(unsigned char* blk, const RowOff& ro, int f0, const uint32_t* hi, const uint32_t* lo) {
 #pragma unroll
-  for (int j = 0; j < 16; ++j) __stcs(reinterpret_cast<float*>(blk + (f0 + j) * 128 + ro.o[(f0 + j) & 7]), v[j] * mul);
+  for (int i = 0; i < 8; ++i) {
+    unsigned char* r0 = blk + (f0 + 2 * i) * 128 + ro.o[(2 * i) & 7];
+    unsigned char* r1 = blk + (f0 + 2 * i + 1) * 128 + ro.o[(2 * i + 1) & 7];
+    st_half(r0, hi[i]);
+    st_half(reinterpret_cast<unsigned char*>(reinterpret_cast<uintptr_t>(r0) ^ 64), lo[i]);
+    st_half(r1, hi[i] >> 16);
+    st_half(reinterpret_cast<unsigned char*>(reinterpret_cast<uintptr_t>(r1) ^ 64), lo[i] >> 16);
+  }
 }
 __device__ __forceinline__ uint32_t positive_bits16(const float* v) {
   uint32_t m = 0;
@@ -90,7 +101,6 @@ __global__ void __launch_bounds__(k3::NT, 2)
   const int d = a.st.d, B = a.B;
   const Small so = small_layout();
   float* sm_small = reinterpret_cast<float*>(smem + SM_SMALL);
-  float* sm_irho = reinterpret_cast<float*>(smem + SM_IRHO);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_SMALL + so.total * 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + N_BARS);
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -149,9 +159,10 @@ __global__ void __launch_bounds__(k3::NT, 2)
         uint64_t m_r1a = 0, m_r1b = 0, m_y1a = 0, m_y1b = 0, m_r2 = 0, m_y2 = 0;
         uint32_t m_r3a = 0, m_r3b = 0;
 
-        // 8 TMEM pieces of 32 columns; this thread handles features [16 h, 16 h + 16) of each: fn(c, v) post-processes
-        // the 16 accumulator values (and stores to the scratch), then they go to shared-memory chunk c if `to_chunk`
-        auto pieces = [&](uint32_t pc_col, bool to_chunk, auto&& fn) {
+        // 8 TMEM pieces of 32 columns; this thread handles features [16 h, 16 h + 16) of each: fn(c, v) post-processes the
+        // 16 accumulator values, the fp16 hi / lo pairs go to feature block fb0 + c of the scratch and, if `to_chunk`,
+        // to shared-memory chunk c
+        auto pieces = [&](uint32_t pc_col, bool to_chunk, int fb0, auto&& fn) {
 #pragma unroll 1
           for (int c = 0; c < 8; ++c) {
             const int b = pu & 1;
@@ -164,9 +175,10 @@ __global__ void __launch_bounds__(k3::NT, 2)
             warp_arrive(&bars[PC_EMPTY + b]);
             ++pu;
             fn(c, v);
+            uint32_t hi[8], lo[8];
+            split16(v, hi, lo);
+            store_fb16(sq + (fb0 + c) * FB_BYTES, ro, 16 * h, hi, lo);
             if (to_chunk) {
-              uint32_t hi[8], lo[8];
-              split16(v, hi, lo);
               const int cb = cu & 1;
               mbar_wait_parked(&bars[CH_EMPTY + cb], ((cu >> 1) & 1) ^ 1);
               store_chunk16(smem + SM_CHUNK + cb * CHUNK_BYTES, p, 2 * h, hi, lo);
@@ -185,16 +197,19 @@ __global__ void __launch_bounds__(k3::NT, 2)
 #pragma unroll
           for (int c = 1; c < KIN; ++c)
             xb[c] = (c - 1 < d && live) ? __ldg(a.states + ((size_t)ti * B + m) * d + (c - 1)) : 0.f;
-          unsigned char* xblk = sq + tc::FB_XIN * FB_BYTES;
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const float val = c < KIN ? xb[c < KIN ? c : 0] : (c == tc::ONES_FEATURE ? 1.0f : 0.f);
-            *reinterpret_cast<float*>(xblk + c * 128 + ro.o[c & 7]) = val;
-          }
 #pragma unroll
           for (int c = 0; c < KIN; ++c) xb[c] *= s_x;
           uint32_t hi[8], lo[8];
           split16(xb, hi, lo);
+          // XIN block of the scratch: features [t, x] s_x, zeros, and the constant 1 (exactly 1.0 in fp16) at ONES_FEATURE
+          unsigned char* xblk = sq + tc::FB_XIN * FB_BYTES;
+          store_fb16(xblk, ro, 0, hi, lo);
+#pragma unroll
+          for (int c = KIN; c < 32; ++c) {
+            unsigned char* row = xblk + c * 128 + ro.o[c & 7];
+            st_half(row, c == tc::ONES_FEATURE ? 0x3C00u : 0u);
+            st_half(reinterpret_cast<unsigned char*>(reinterpret_cast<uintptr_t>(row) ^ 64), 0u);
+          }
           unsigned char* base = smem + SM_XIN + (p % 8) * 16 + (p / 8) * 128;
           *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(base + 2048) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
@@ -205,15 +220,14 @@ __global__ void __launch_bounds__(k3::NT, 2)
         }
         // ---- F1: r1 chunks for down_1 (+ mask, + scratch)
         {
-          const float inv = sm_small[so.invs + 0], us = 1.f / sm_small[so.sa + A_R1];
-          pieces(C_PC, true, [&](int c, float* v) {
+          const float inv = sm_small[so.invs + 0];
+          pieces(C_PC, true, tc::FB_R1, [&](int c, float* v) {
             const float* bias = sm_small + so.b_d0 + 32 * c + 16 * h;
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = fmaxf(fmaf(v[j], inv, bias[j]), 0.f);
             const uint64_t bits = (uint64_t)positive_bits16(v) << (16 * (c & 3));
             if (c < 4) m_r1a |= bits;
             else m_r1b |= bits;
-            store_fb16(sq + (tc::FB_R1 + c) * FB_BYTES, ro, 16 * h, v, us);
           });
         }
         // ---- F2: r2 in place; helpers keep the Wc r1 accumulator
@@ -225,7 +239,7 @@ __global__ void __launch_bounds__(k3::NT, 2)
           tmem_wait_ld();
         }
         {
-          const float inv = sm_small[so.invs + 1], us = 1.f / sm_small[so.sa + A_R2];
+          const float inv = sm_small[so.invs + 1];
 #pragma unroll 1
           for (int i = 0; i < 4; ++i) {
             const int gq = 2 * i + h;
@@ -239,7 +253,7 @@ __global__ void __launch_bounds__(k3::NT, 2)
             uint32_t hi[8], lo[8];
             split16(v, hi, lo);
             store_group16(lane_t + C_SA + 16 * gq, hi, lo);
-            store_fb16(sq + (tc::FB_R2 + (gq >> 1)) * FB_BYTES, ro, 16 * (gq & 1), v, us);
+            store_fb16(sq + (tc::FB_R2 + (gq >> 1)) * FB_BYTES, ro, 16 * (gq & 1), hi, lo);
             if (i == 1) {
               tmem_wait_st();
               fence_before_sync();
@@ -254,7 +268,7 @@ __global__ void __launch_bounds__(k3::NT, 2)
         mbar_wait_parked(&bars[D2_FULL], ph);
         fence_after_sync();
         {
-          const float inv = sm_small[so.invs + 2], us = 1.f / sm_small[so.sa + A_R3];
+          const float inv = sm_small[so.invs + 2];
 #pragma unroll 1
           for (int i = 0; i < 2; ++i) {
             float v[16];
@@ -268,7 +282,7 @@ __global__ void __launch_bounds__(k3::NT, 2)
             uint32_t hi[8], lo[8];
             split16(v, hi, lo);
             store_chunk16(smem + SM_CHUNK + h * CHUNK_BYTES, p, 2 * i, hi, lo);
-            store_fb16(sq + (tc::FB_R3 + h) * FB_BYTES, ro, 16 * i, v, us);
+            store_fb16(sq + (tc::FB_R3 + h) * FB_BYTES, ro, 16 * i, hi, lo);
           }
         }
         fence_before_sync();
@@ -278,7 +292,7 @@ __global__ void __launch_bounds__(k3::NT, 2)
         mbar_wait_parked(&bars[D3_FULL], ph);
         fence_after_sync();
         {
-          const float inv_u2 = sm_small[so.invs + 6], inv_r2 = sm_small[so.invs + 5], us = 1.f / sm_small[so.sa + A_O2];
+          const float inv_u2 = sm_small[so.invs + 6], inv_r2 = sm_small[so.invs + 5];
 #pragma unroll 1
           for (int i = 0; i < 4; ++i) {
             const int gq = 2 * i + h;
@@ -296,7 +310,7 @@ __global__ void __launch_bounds__(k3::NT, 2)
             uint32_t hi[8], lo[8];
             split16(y, hi, lo);
             store_group16(lane_t + C_SA + 16 * gq, hi, lo);
-            store_fb16(sq + (tc::FB_O2 + (gq >> 1)) * FB_BYTES, ro, 16 * (gq & 1), y, us);
+            store_fb16(sq + (tc::FB_O2 + (gq >> 1)) * FB_BYTES, ro, 16 * (gq & 1), hi, lo);
           }
           tmem_wait_st();
           fence_before_sync();
@@ -304,15 +318,14 @@ __global__ void __launch_bounds__(k3::NT, 2)
         }
         // ---- F6: y1 = relu(D4 + b_u1) -> A chunks of the folded up_0 (+ mask, + scratch)
         {
-          const float inv = sm_small[so.invs + 7], us = 1.f / sm_small[so.sa + A_Y1];
-          pieces(C_PC, true, [&](int c, float* v) {
+          const float inv = sm_small[so.invs + 7];
+          pieces(C_PC, true, tc::FB_Y1, [&](int c, float* v) {
             const float* bias = sm_small + so.b_u1 + 32 * c + 16 * h;
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = fmaxf(fmaf(v[j], inv, bias[j]), 0.f);
             const uint64_t bits = (uint64_t)positive_bits16(v) << (16 * (c & 3));
             if (c < 4) m_y1a |= bits;
             else m_y1b |= bits;
-            store_fb16(sq + (tc::FB_Y1 + c) * FB_BYTES, ro, 16 * h, v, us);
           });
         }
         // ---- F8: y0 = W_u0 y1 (TMEM) + Wc r1 (helper registers) + bc -> owners, through the exchange area
@@ -380,30 +393,30 @@ __global__ void __launch_bounds__(k3::NT, 2)
                 if (j < d) dv[j] = dl[j];
             }
           }
-          // rho = 2^(127 - e) with e the biased exponent of max |dv|: the largest entry of rho dv lies in [1, 2)
-          float mx = 0.f;
+          // d_y0 = 1[y0 > 0] dv and d_o0 = dv, both x the global gradient scale: operand of the backward pass + scratch
+          const float s_g = sm_small[so.sb + B_DY0];
+          float dy[KIN], dz[KIN];
 #pragma unroll
-          for (int j = 0; j < KIN; ++j) mx = fmaxf(mx, fabsf(dv[j]));
-          uint32_t e = (__float_as_uint(mx) >> 23) & 0xffu;
-          e = e < 2u ? 127u : (e > 252u ? 127u : e);   // zero / denormal gradients (masked points) and inf: leave unscaled
-          const float rho = __uint_as_float((254u - e) << 23), irho = __uint_as_float(e << 23);
-          sm_irho[p] = irho;
-          float dy[KIN];
+          for (int c = 0; c < KIN; ++c) {
+            dz[c] = dv[c] * s_g;
+            dy[c] = y0[c] > 0.f ? dz[c] : 0.f;
+          }
+          uint32_t hi[8], lo[8], zh[8], zl[8];
+          split16(dy, hi, lo);
+          split16(dz, zh, zl);
           unsigned char* yblk = sq + tc::FB_DY0 * FB_BYTES;
           unsigned char* zblk = sq + tc::FB_DO0 * FB_BYTES;
+          store_fb16(yblk, ro, 0, hi, lo);
+          store_fb16(zblk, ro, 0, zh, zl);
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            float vy = 0.f, vz = 0.f;
-            if (c < KIN) {
-              vz = dv[c < KIN ? c : 0];                               // d_o0
-              vy = y0[c < KIN ? c : 0] > 0.f ? vz : 0.f;              // d_y0
-              dy[c < KIN ? c : 0] = vy * rho * sm_small[so.sb + B_DY0];
-            }
-            *reinterpret_cast<float*>(yblk + c * 128 + ro.o[c & 7]) = vy;
-            *reinterpret_cast<float*>(zblk + c * 128 + ro.o[c & 7]) = vz;
+          for (int c = KIN; c < 32; ++c) {
+            unsigned char* ry = yblk + c * 128 + ro.o[c & 7];
+            unsigned char* rz = zblk + c * 128 + ro.o[c & 7];
+            st_half(ry, 0u);
+            st_half(reinterpret_cast<unsigned char*>(reinterpret_cast<uintptr_t>(ry) ^ 64), 0u);
+            st_half(rz, 0u);
+            st_half(reinterpret_cast<unsigned char*>(reinterpret_cast<uintptr_t>(rz) ^ 64), 0u);
           }
-          uint32_t hi[8], lo[8];
-          split16(dy, hi, lo);
           unsigned char* base = smem + SM_XIN + (p % 8) * 16 + (p / 8) * 128;
           *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(base + 2048) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
@@ -412,23 +425,22 @@ __global__ void __launch_bounds__(k3::NT, 2)
           fence_async_smem();
           warp_arrive(&bars[DY0_FULL]);
         }
-        e_sync();   // sm_irho is visible to the helpers; the exchange area is chunk buffer 0 again
-        const float irho = sm_irho[p];
+        // (no second e_sync: the helpers cannot write chunk buffer 0 -- the exchange area -- before the first d_o1 piece
+        //  exists, and that needs DY0_FULL from all four owner warps, who have read the exchange area by then)
         // ---- B1: d_y1 = m_y1 . d_o1 chunks (d_y1 -> scratch)
         {
-          const float f = sm_small[so.bf + P_U0T], tmul = irho / sm_small[so.sb + B_DY1];
-          pieces(C_PC, true, [&](int c, float* v) {
+          const float f = sm_small[so.bf + P_U0T];
+          pieces(C_PC, true, tc::FB_DY1, [&](int c, float* v) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] *= f;
             apply_bits16(v, (uint32_t)((c < 4 ? m_y1a : m_y1b) >> (16 * (c & 3))));
-            store_fb16(sq + (tc::FB_DY1 + c) * FB_BYTES, ro, 16 * h, v, tmul);
           });
         }
         // ---- B2: d_o2 -> A operand in place; d_y2 = m_y2 . d_o2 -> chunks for up_2^T; both -> scratch
         mbar_wait_parked(&bars[BDO2_FULL], ph);
         fence_after_sync();
         {
-          const float f = sm_small[so.bf + P_U1T], tmul = irho / sm_small[so.sb + B_DO2];
+          const float f = sm_small[so.bf + P_U1T];
 #pragma unroll 1
           for (int i = 0; i < 4; ++i) {
             const int gq = 2 * i + h;
@@ -440,10 +452,10 @@ __global__ void __launch_bounds__(k3::NT, 2)
             uint32_t hi[8], lo[8];
             split16(v, hi, lo);
             store_group16(lane_t + C_SA + 16 * gq, hi, lo);
-            store_fb16(sq + (tc::FB_DO2 + (gq >> 1)) * FB_BYTES, ro, 16 * (gq & 1), v, tmul);
+            store_fb16(sq + (tc::FB_DO2 + (gq >> 1)) * FB_BYTES, ro, 16 * (gq & 1), hi, lo);
             apply_bits16(v, (uint32_t)(m_y2 >> (16 * i)));
-            store_fb16(sq + (tc::FB_DY2 + (gq >> 1)) * FB_BYTES, ro, 16 * (gq & 1), v, tmul);
             split16(v, hi, lo);
+            store_fb16(sq + (tc::FB_DY2 + (gq >> 1)) * FB_BYTES, ro, 16 * (gq & 1), hi, lo);
             const int cb = cu & 1;   // chunk i = features [32 i, 32 i + 32): group 2 i from half 0, 2 i + 1 from half 1
             mbar_wait_parked(&bars[CH_EMPTY + cb], ((cu >> 1) & 1) ^ 1);
             store_chunk16(smem + SM_CHUNK + cb * CHUNK_BYTES, p, 2 * h, hi, lo);
@@ -459,7 +471,7 @@ __global__ void __launch_bounds__(k3::NT, 2)
         mbar_wait_parked(&bars[BD3_FULL], ph);
         fence_after_sync();
         {
-          const float f = sm_small[so.bf + P_U2T], tmul = irho / sm_small[so.sb + B_DZ3];
+          const float f = sm_small[so.bf + P_U2T];
 #pragma unroll 1
           for (int i = 0; i < 2; ++i) {
             float v[16];
@@ -471,7 +483,7 @@ __global__ void __launch_bounds__(k3::NT, 2)
             uint32_t hi[8], lo[8];
             split16(v, hi, lo);
             store_chunk16(smem + SM_CHUNK + h * CHUNK_BYTES, p, 2 * i, hi, lo);
-            store_fb16(sq + (tc::FB_DZ3 + h) * FB_BYTES, ro, 16 * i, v, tmul);
+            store_fb16(sq + (tc::FB_DZ3 + h) * FB_BYTES, ro, 16 * i, hi, lo);
           }
         }
         fence_before_sync();
@@ -481,7 +493,7 @@ __global__ void __launch_bounds__(k3::NT, 2)
         mbar_wait_parked(&bars[BR2_FULL], ph);
         fence_after_sync();
         {
-          const float f = sm_small[so.bf + P_R2T], tmul = irho / sm_small[so.sb + B_DZ2];
+          const float f = sm_small[so.bf + P_R2T];
 #pragma unroll 1
           for (int i = 0; i < 4; ++i) {
             const int gq = 2 * i + h;
@@ -495,7 +507,7 @@ __global__ void __launch_bounds__(k3::NT, 2)
             uint32_t hi[8], lo[8];
             split16(v, hi, lo);
             store_group16(lane_t + col, hi, lo);
-            store_fb16(sq + (tc::FB_DZ2 + (gq >> 1)) * FB_BYTES, ro, 16 * (gq & 1), v, tmul);
+            store_fb16(sq + (tc::FB_DZ2 + (gq >> 1)) * FB_BYTES, ro, 16 * (gq & 1), hi, lo);
           }
           tmem_wait_st();
           fence_before_sync();
@@ -503,10 +515,11 @@ __global__ void __launch_bounds__(k3::NT, 2)
         }
         // ---- B7: d_z1 = m_r1 . d_r1 -> scratch
         {
-          const float tmul = irho * sm_small[so.bt + P_D1T];
-          pieces(C_BPC, false, [&](int c, float* v) {
+          const float f = sm_small[so.bf + P_D1T];
+          pieces(C_BPC, false, tc::FB_DZ1, [&](int c, float* v) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] *= f;
             apply_bits16(v, (uint32_t)((c < 4 ? m_r1a : m_r1b) >> (16 * (c & 3))));
-            store_fb16(sq + (tc::FB_DZ1 + c) * FB_BYTES, ro, 16 * h, v, tmul);
           });
         }
       }
@@ -773,8 +786,10 @@ int launch_loss_h(const LossArgs& a, const socm_unet* net, float* grad, void* wo
   c.B = a.B;
   c.K = a.K;
   c.ldt = a.ldt;
+  c.w = a.w;
   c.n_samples = 512;
   c.lmbd = a.st.lmbd;
+  c.loss_scale = a.scale;
   if (int rc = setup_h(net, ws, c, true, stream)) return rc;
   SOCM_CUDA(cudaMemsetAsync(aux, 0, tc::AUX_FLOATS * sizeof(float), stream));
   const int smem = loss_h_smem_bytes();
@@ -787,7 +802,7 @@ int launch_loss_h(const LossArgs& a, const socm_unet* net, float* grad, void* wo
     const int grid = nt < 2 * sm_count() ? nt : 2 * sm_count();
     loss_h_kernel<<<grid, k3::NT, smem, stream>>>(a, ws, small_ptr(ws), scratch, (int)t0, nt);
     SOCM_LAUNCH_CHECK();
-    if (int rc = tc::launch_wgrad_tc(scratch, nt, a.st.d, grad, aux, stream)) return rc;
+    if (int rc = launch_wgrad_h(scratch, nt, a.st.d, small_ptr(ws) + small_layout().sk, grad, aux, stream)) return rc;
   }
   tc::fold_finish_kernel<<<H0, H0, 0, stream>>>(*net, aux, grad);
   SOCM_LAUNCH_CHECK();

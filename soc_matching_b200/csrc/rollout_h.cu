@@ -56,12 +56,19 @@ __device__ __forceinline__ void warp_max_to(uint32_t* slot, float v) {
 //       Philox normal z, at t in {0, T/3, 2T/3, T} -- the scale only has to be right within ~2^10 (head room) upwards
 //       and ~2^15 downwards (precision floor), see unet_h.cuh;
 //   loss mode: points of the stored trajectories, strided over all (K+1) B of them.
-constexpr int CALIB_BWD_FLOATS = 32 + H0 + 2 * H1 + H2;
+constexpr int CALIB_BWD_FLOATS = 32 + 2 * H0 + 2 * H1 + H2;
 __global__ void __launch_bounds__(256) calib_h_kernel(socm_unet net, const float* __restrict__ wc, CalibArgs c,
                                                       uint32_t* __restrict__ mx) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* smem = reinterpret_cast<float*>(smem_raw);
   const int d = net.d, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == 10) {  // max |w_m| over all paths (exact: the global scale of the loss gradient hangs on it)
+    float v = 0.f;
+    if (c.w != nullptr)
+      for (int i = threadIdx.x; i < c.B; i += blockDim.x) v = fmaxf(v, fabsf(__ldg(c.w + i)));
+    warp_max_to(mx + MX_W, v);
+    return;
+  }
   if (blockIdx.x < 10) {  // weight maxima
     const int l = blockIdx.x;
     const int nout[10] = {H0, H1, H2, d, H0, H1, H1, H0, d, d};
@@ -74,7 +81,7 @@ __global__ void __launch_bounds__(256) calib_h_kernel(socm_unet net, const float
   }
   const int per_warp = generic::fwd_floats(d, H0, H1, H2) + CALIB_BWD_FLOATS;
   generic::FwdBuf b = generic::carve_fwd(smem + (size_t)warp * per_warp, d, H0, H1, H2);
-  for (int i = (blockIdx.x - 10) * 8 + warp; i < c.n_samples; i += (gridDim.x - 10) * 8) {
+  for (int i = (blockIdx.x - 11) * 8 + warp; i < c.n_samples; i += (gridDim.x - 11) * 8) {
     if (c.states == nullptr) {
       const int nb = c.B < 64 ? c.B : 64;
       const int m = i % nb, v = (i / nb) & 3;
@@ -132,6 +139,7 @@ __global__ void __launch_bounds__(256) calib_h_kernel(socm_unet net, const float
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) dvm = fmaxf(dvm, __shfl_xor_sync(0xffffffffu, dvm, o));
+      if (lane == 0 && dvm > 0.f) atomicMax(mx + MX_DIFF, __float_as_uint(dvm));
       if (dvm > 0.f) {
         __syncwarp();
         for (int j = lane; j < d; j += 32) d_y0[j] = b.y0[j] > 0.f ? d_y0[j] / dvm : 0.f;
@@ -158,6 +166,17 @@ __global__ void __launch_bounds__(256) calib_h_kernel(socm_unet net, const float
         for (int k = lane; k < H1; k += 32) d_r2[k] = b.r2[k] > 0.f ? d_r2[k] : 0.f;   // d_z2
         __syncwarp();
         warp_max_to(mx + MX_B + B_DZ2, amax(d_r2, H1, false));
+        // d_z1 = m_r1 . (W_d1^T d_z2 + W_r1^T d_o1),  d_o1 = W_u0^T d_y0 (recomputed: the buffer now holds d_y1)
+        float* d_r1 = bw + 32 + H0 + 2 * H1 + H2;   // [H0]
+        generic::dense_t(net.w[8], d, H0, d_y0, d_o1, false, lane);
+        __syncwarp();
+        generic::dense_t(net.w[4], H0, H0, d_o1, d_r1, false, lane);
+        __syncwarp();
+        generic::dense_t(net.w[1], H1, H0, d_r2, d_r1, true, lane);
+        __syncwarp();
+        for (int k = lane; k < H0; k += 32) d_r1[k] = b.r1[k] > 0.f ? d_r1[k] : 0.f;
+        __syncwarp();
+        warp_max_to(mx + MX_B + B_DZ1, amax(d_r1, H0, false));
       }
       __syncwarp();
     }
@@ -169,14 +188,22 @@ __global__ void __launch_bounds__(256) calib_h_kernel(socm_unet net, const float
 struct Scales {
   float sa[N_ACT], sw[N_WSCALE], sb[N_BACT];
 };
-__device__ __forceinline__ Scales make_scales(const uint32_t* __restrict__ mx) {
+__device__ __forceinline__ Scales make_scales(const uint32_t* __restrict__ mx, float loss_scale) {
   Scales z;
   for (int a = 0; a < N_ACT; ++a) z.sa[a] = pow2_scale(__uint_as_float(mx[a]), ACT_TARGET);
   for (int l = 0; l < 10; ++l) z.sw[l] = pow2_scale(__uint_as_float(mx[N_ACT + l]), W_TARGET);
-  z.sb[B_DY0] = pow2_scale(2.f, ACT_TARGET);
+  // Loss gradient dv = 2 s w scale (nabla_V - target): bounded by 2 |scale| max|w| (exact) x max|diff| (sampled, x8 margin).
+  // One GLOBAL power-of-two scale maps that bound to 4096 (16x of fp16 head room left): the hi / lo pairs of every
+  // gradient tensor then serve K3a's own dgrad MMAs and, unchanged, K3b's contraction over the points.  Rows far below
+  // the bound lose relative precision (absolute error 2^-25 / scale), in proportion to how little they add to the sum.
+  float wmax = __uint_as_float(mx[MX_W]), dmax = __uint_as_float(mx[MX_DIFF]);
+  wmax = wmax > 0.f ? wmax : 1.f;
+  dmax = dmax > 0.f ? dmax : 1.f;
+  const float bound = 2.f * fabsf(loss_scale) * wmax * dmax * 8.f;
+  z.sb[B_DY0] = pow2_scale(bound, 4096.f);
   for (int a = B_DY1; a < N_BACT; ++a) {
     const float g = __uint_as_float(mx[MX_B + a]);
-    z.sb[a] = pow2_scale(g > 0.f ? 2.f * g : 2.f, ACT_TARGET);
+    z.sb[a] = pow2_scale(bound * (g > 0.f ? g : 1.f), 4096.f);
   }
   // products that accumulate onto another product's accumulator arrive in its units; if that pushes the weight block
   // out of the comfortable fp16 range, move the operand scale instead (it has 2^10 of head room and a 2^15 window)
@@ -192,11 +219,11 @@ __device__ __forceinline__ Scales make_scales(const uint32_t* __restrict__ mx) {
 }
 
 __global__ void pack_h_kernel(socm_unet net, const float* __restrict__ wc, const uint32_t* __restrict__ mx,
-                              unsigned char* __restrict__ tape, float* __restrict__ small, int with_bwd) {
+                              unsigned char* __restrict__ tape, float* __restrict__ small, int with_bwd, float loss_scale) {
   const int d = net.d;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   const Small so = small_layout();
-  const Scales z = make_scales(mx);
+  const Scales z = make_scales(mx, loss_scale);
   const int n_items = FWD_ITEMS + (with_bwd ? BWD_ITEMS : 0);
   for (int it = 0; it < n_items; ++it) {
     const PackItem pi = it < FWD_ITEMS ? fwd_item(d, it) : bwd_item(d, it - FWD_ITEMS);
@@ -243,11 +270,14 @@ __global__ void pack_h_kernel(socm_unet net, const float* __restrict__ wc, const
     // accumulator units of the five backward products: s_in * w
     const float unit[N_BPROD] = {z.sb[B_DY0] * z.sw[8], z.sb[B_DY1] * z.sw[7], z.sb[B_DO2] * z.sw[6], z.sb[B_DO2] * z.sw[5],
                                  z.sb[B_DZ2] * z.sw[1]};
-    const float s_out[N_BPROD] = {z.sb[B_DY1], z.sb[B_DO2], z.sb[B_DZ3], z.sb[B_DZ2], 1.f};
+    const float s_out[N_BPROD] = {z.sb[B_DY1], z.sb[B_DO2], z.sb[B_DZ3], z.sb[B_DZ2], z.sb[B_DZ1]};
     for (int q = 0; q < N_BPROD; ++q) {
       small[so.bt + q] = 1.f / unit[q];
       small[so.bf + q] = s_out[q] / unit[q];
     }
+    const float sk[N_SCRATCH_T] = {z.sa[A_X], z.sa[A_R1], z.sa[A_R2], z.sa[A_R3], z.sa[A_O2], z.sa[A_Y1], z.sb[B_DY0], z.sb[B_DY0],
+                                   z.sb[B_DY1], z.sb[B_DO2], z.sb[B_DO2], z.sb[B_DZ3], z.sb[B_DZ2], z.sb[B_DZ1]};
+    for (int t = 0; t < N_SCRATCH_T; ++t) small[so.sk + t] = sk[t];
   }
 }
 
@@ -260,9 +290,9 @@ int setup_h(const socm_unet* net, unsigned char* ws, const CalibArgs& c, bool wi
   SOCM_LAUNCH_CHECK();
   const size_t smem = 8 * (size_t)(generic::fwd_floats(net->d, H0, H1, H2) + CALIB_BWD_FLOATS) * sizeof(float);
   SOCM_CUDA(cudaFuncSetAttribute(calib_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  calib_h_kernel<<<10 + (c.n_samples + 7) / 8, 256, smem, stream>>>(*net, wc, c, mx);
+  calib_h_kernel<<<11 + (c.n_samples + 7) / 8, 256, smem, stream>>>(*net, wc, c, mx);
   SOCM_LAUNCH_CHECK();
-  pack_h_kernel<<<96, 256, 0, stream>>>(*net, wc, mx, ws, small, with_bwd ? 1 : 0);
+  pack_h_kernel<<<96, 256, 0, stream>>>(*net, wc, mx, ws, small, with_bwd ? 1 : 0, c.loss_scale);
   SOCM_LAUNCH_CHECK();
   return SOCM_OK;
 }

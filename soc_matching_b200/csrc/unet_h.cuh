@@ -161,9 +161,12 @@ struct Small {
   int sb;    // [N_BACT]  scales of the backward operands d_y0, d_y1, d_o2 (= d_y2), d_z3, d_z2
   int bf;    // [N_BPROD] acc -> next operand:   s_out / (s_in w)
   int bt;    // [N_BPROD] acc -> normalised true value: 1 / (s_in w)
+  int sk;    // [N_SCRATCH_T] scale of every tensor of the fp16 scratch (ScratchT), read by K3b's flush (wgrad_h.cu)
   int total;
 };
-enum BAct { B_DY0 = 0, B_DY1, B_DO2, B_DZ3, B_DZ2, N_BACT };
+enum BAct { B_DY0 = 0, B_DY1, B_DO2, B_DZ3, B_DZ2, B_DZ1, N_BACT };
+// tensors of the K3a -> K3b scratch, in the order of their feature blocks (loss_tc.cuh)
+enum ScratchT { T_XIN = 0, T_R1, T_R2, T_R3, T_O2, T_Y1, T_DY0, T_DO0, T_DY1, T_DY2, T_DO2, T_DZ3, T_DZ2, T_DZ1, N_SCRATCH_T };
 enum BProd { P_U0T = 0, P_U1T, P_U2T, P_R2T, P_D1T, N_BPROD };   // d_o1, d_o2, d_r3, d_r2 (res_2^T + down_2^T), d_r1
 __host__ __device__ inline Small small_layout() {
   Small o;
@@ -183,6 +186,7 @@ __host__ __device__ inline Small small_layout() {
   o.sb = p; p += 8;
   o.bf = p; p += 8;
   o.bt = p; p += 8;
+  o.sk = p; p += 16;
   o.total = ((p + 3) / 4) * 4;
   return o;
 }
@@ -224,7 +228,9 @@ __host__ __device__ inline float* small_ptr(unsigned char* ws) { return reinterp
 __host__ __device__ inline float* wc_ptr(unsigned char* ws) { return small_ptr(ws) + small_layout().total; }
 __host__ __device__ inline uint32_t* max_ptr(unsigned char* ws) { return reinterpret_cast<uint32_t*>(wc_ptr(ws) + WC_FLOATS); }
 // max buffer slots: [0, N_ACT) forward activations, [N_ACT, N_ACT + 10) weights, [MX_B, MX_B + N_BACT) backward gains
-constexpr int MX_B = 24;
+// (max |d_layer| per unit of max |d loss / d nabla_V| of the same point), MX_W = max |w_m| over all paths (exact),
+// MX_DIFF = max |nabla_V - target| over the sample points
+constexpr int MX_B = 24, MX_W = 40, MX_DIFF = 41;
 
 // power-of-two scale that maps `mx` into [target / 2, target)
 __host__ __device__ inline float pow2_scale(float mx, float target) {
@@ -323,9 +329,12 @@ struct CalibArgs {
   const float* states;    // loss mode [K+1][B][d]
   const float* ts;        // loss mode [K+1]
   const float* target;    // loss mode [B][ldt]
+  const float* w;         // loss mode [B] path weights (importance weights or dF/dS_m of the path functionals)
   int B, K, ldt, n_samples;
-  float lmbd;
+  float lmbd, loss_scale;
 };
+int launch_wgrad_h(const unsigned char* scratch, int n_tiles, int d, const float* scales, float* grad, float* aux,
+                   cudaStream_t stream);
 int setup_h(const socm_unet* net, unsigned char* ws, const CalibArgs& c, bool with_bwd, cudaStream_t stream);
 
 }  // namespace hx
