@@ -1,9 +1,10 @@
 // loss_h.cu -- K3a on the fp16-split tcgen05 engine (unet_h.cuh), two CTAs per SM: UNet forward at 128 trajectory points,
 // weighted loss and the whole dgrad chain.  Replaces method.py:272-287 (nabla_V at all points), 692-720 (loss) and the
 // activation-gradient half of loss.backward() (main.py:323); the weight gradients are K3b (wgrad_h.cu), which reads the
-// operands this kernel leaves in the scratch: the geometry of loss_tc.cuh, but every feature row holds the 32 points of
-// its tile quarter as [fp16 hi x 32 | fp16 lo x 32] of the operand-scaled value -- the hi / lo pairs this kernel computes
-// for its own MMAs anyway, so the scratch costs two 2-byte stores per value and K3b needs no split pass.
+// operands this kernel leaves in the scratch: tile -> 4 quarters -> 59 feature blocks of 4 KB as in loss_tc.cuh, but a block
+// holds fp16 hi and lo planes of the operand-scaled values in the no-swizzle MN-major core-matrix layout (store_fb16 below)
+// -- the hi / lo pairs this kernel computes for its own MMAs anyway, so the scratch costs one 16-byte store per 8 values at
+// a compile-time offset, and K3b needs no split pass.
 //
 // A tile is 128 consecutive paths at one grid time t_i.  Forward = the rollout's forward (rollout_h.cu) from the stored
 // state, ReLU masks kept in registers.  Backward = its mirror image on the transposed weight tape.  The loss gradient
@@ -55,31 +56,33 @@ constexpr uint32_t C_DR3 = 0, C_DR2A = 0, C_DR2B = 192, C_BPC = 64;   // backwar
 
 __host__ __device__ inline int loss_h_smem_bytes() { return k3::SM_SMALL + small_layout().total * 4 + k3::N_BARS * 8 + 16; }
 
-// Scratch stores: thread <-> point r of the quarter.  Row of feature f (128 bytes, 16-byte chunks XOR-permuted by
-// k = f & 7): the hi half of point r sits in logical chunk r >> 3, the lo half in chunk 4 + (r >> 3), at 2 (r & 7)
-// inside the chunk.  `ro.o[k]` = byte offset of the hi half inside the row; the lo half is that offset ^ 64.
-struct RowOff {
-  int o[8];
-  __device__ __forceinline__ explicit RowOff(int r) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = ((((r >> 3) ^ k) & 7) << 4) + 2 * (r & 7);
-  }
-};
-__device__ __forceinline__ void st_half(unsigned char* p, uint32_t v) {
-  __stcs(reinterpret_cast<unsigned short*>(p), (unsigned short)v);
+// Scratch stores: thread <-> point r of the quarter.  A feature block (32 features x 32 points, fp16 hi and lo) is four
+// groups of 8 features x 1 KB in the canonical no-swizzle MN-MAJOR layout of tcgen05 (K = points, MN = features): per group
+// eight 128-byte core matrices of 8 points x (8 features = 16 bytes), point groups 0..3 = hi plane, 4..7 = lo plane:
+//     byte(f, r, plane) = (f / 8) * 1024 + plane * 512 + r * 16 + (f % 8) * 2 .
+// A thread owns one point and holds packed pairs of neighbouring features, so eight features of one plane are ONE 16-byte
+// store at a compile-time offset from (block + r * 16), and a warp's store covers 512 contiguous bytes.  (A K-major
+// scratch needs one 2-byte store per value: ~8x the LSU wavefronts, which bounded this kernel.)
+__device__ __forceinline__ int row_off(int r) { return r * 16; }
+__device__ __forceinline__ void st_q(unsigned char* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  __stcs(reinterpret_cast<uint4*>(p), make_uint4(a, b, c, d));
 }
-// features [f0, f0 + 16) of feature block `blk` from the packed pairs hi[i] / lo[i] = features (f0 + 2 i, f0 + 2 i + 1)
-// (f0 a multiple of 16: the chunk permutation index of feature f0 + j is j & 7)
-__device__ __forceinline__ void store_fb16(unsigned char* blk, const RowOff& ro, int f0, const uint32_t* hi, const uint32_t* lo) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    unsigned char* r0 = blk + (f0 + 2 * i) * 128 + ro.o[(2 * i) & 7];
-    unsigned char* r1 = blk + (f0 + 2 * i + 1) * 128 + ro.o[(2 * i + 1) & 7];
-    st_half(r0, hi[i]);
-    st_half(reinterpret_cast<unsigned char*>(reinterpret_cast<uintptr_t>(r0) ^ 64), lo[i]);
-    st_half(r1, hi[i] >> 16);
-    st_half(reinterpret_cast<unsigned char*>(reinterpret_cast<uintptr_t>(r1) ^ 64), lo[i] >> 16);
-  }
+// features [f0, f0 + 16) of the feature block at `blk` (already offset by row_off) from the packed pairs
+// hi[i] / lo[i] = features (f0 + 2 i, f0 + 2 i + 1); f0 a multiple of 16
+__device__ __forceinline__ void store_fb16(unsigned char* blk, int f0, const uint32_t* hi, const uint32_t* lo) {
+  unsigned char* g = blk + (f0 >> 3) * 1024;
+  st_q(g, hi[0], hi[1], hi[2], hi[3]);
+  st_q(g + 512, lo[0], lo[1], lo[2], lo[3]);
+  st_q(g + 1024, hi[4], hi[5], hi[6], hi[7]);
+  st_q(g + 1536, lo[4], lo[5], lo[6], lo[7]);
+}
+// features [KIN, 32) of a d-sized block: zeros, except the constant-1 feature (hi = 1.0) when `ones`
+__device__ __forceinline__ void store_fb_tail(unsigned char* blk, bool ones) {
+  static_assert(KIN == 16 && tc::ONES_FEATURE == 31, "tail layout");
+  st_q(blk + 2048, 0u, 0u, 0u, 0u);
+  st_q(blk + 2048 + 512, 0u, 0u, 0u, 0u);
+  st_q(blk + 3072, 0u, 0u, 0u, ones ? 0x3C000000u : 0u);
+  st_q(blk + 3072 + 512, 0u, 0u, 0u, 0u);
 }
 __device__ __forceinline__ uint32_t positive_bits16(const float* v) {
   uint32_t m = 0;
@@ -140,7 +143,6 @@ __global__ void __launch_bounds__(k3::NT, 2)
     auto e_program = [&](auto h_const) {
       constexpr int h = decltype(h_const)::value;   // column half; h == 0 threads own the point
       const int p = tid & (TP - 1), r = tid & 31, q = (tid >> 5) & 3;
-      const RowOff ro(r);
       const uint32_t lane_t = tm + ((uint32_t)(q * 32) << 16);
       uint32_t g = 0;    // tiles done
       uint32_t cu = 0;   // shared-memory chunks produced (ring)
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(k3::NT, 2)
         const int m = m0 + p;
         const bool live = m < B;
         const uint32_t ph = g & 1;
-        unsigned char* sq = scratch + (size_t)lt * TILE_BYTES + (size_t)q * QUARTER_BYTES;   // this warp's quarter
+        unsigned char* sq = scratch + (size_t)lt * TILE_BYTES + (size_t)q * QUARTER_BYTES + row_off(r);   // this warp's quarter, this thread's point
         uint64_t m_r1a = 0, m_r1b = 0, m_y1a = 0, m_y1b = 0, m_r2 = 0, m_y2 = 0;
         uint32_t m_r3a = 0, m_r3b = 0;
 
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(k3::NT, 2)
             fn(c, v);
             uint32_t hi[8], lo[8];
             split16(v, hi, lo);
-            store_fb16(sq + (fb0 + c) * FB_BYTES, ro, 16 * h, hi, lo);
+            store_fb16(sq + (fb0 + c) * FB_BYTES, 16 * h, hi, lo);
             if (to_chunk) {
               const int cb = cu & 1;
               mbar_wait_parked(&bars[CH_EMPTY + cb], ((cu >> 1) & 1) ^ 1);
@@ -203,13 +205,8 @@ __global__ void __launch_bounds__(k3::NT, 2)
           split16(xb, hi, lo);
           // XIN block of the scratch: features [t, x] s_x, zeros, and the constant 1 (exactly 1.0 in fp16) at ONES_FEATURE
           unsigned char* xblk = sq + tc::FB_XIN * FB_BYTES;
-          store_fb16(xblk, ro, 0, hi, lo);
-#pragma unroll
-          for (int c = KIN; c < 32; ++c) {
-            unsigned char* row = xblk + c * 128 + ro.o[c & 7];
-            st_half(row, c == tc::ONES_FEATURE ? 0x3C00u : 0u);
-            st_half(reinterpret_cast<unsigned char*>(reinterpret_cast<uintptr_t>(row) ^ 64), 0u);
-          }
+          store_fb16(xblk, 0, hi, lo);
+          store_fb_tail(xblk, true);
           unsigned char* base = smem + SM_XIN + (p % 8) * 16 + (p / 8) * 128;
           *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(base + 2048) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
@@ -253,7 +250,7 @@ __global__ void __launch_bounds__(k3::NT, 2)
             uint32_t hi[8], lo[8];
             split16(v, hi, lo);
             store_group16(lane_t + C_SA + 16 * gq, hi, lo);
-            store_fb16(sq + (tc::FB_R2 + (gq >> 1)) * FB_BYTES, ro, 16 * (gq & 1), hi, lo);
+            store_fb16(sq + (tc::FB_R2 + (gq >> 1)) * FB_BYTES, 16 * (gq & 1), hi, lo);
             if (i == 1) {
               tmem_wait_st();
               fence_before_sync();
@@ -282,7 +279,7 @@ __global__ void __launch_bounds__(k3::NT, 2)
             uint32_t hi[8], lo[8];
             split16(v, hi, lo);
             store_chunk16(smem + SM_CHUNK + h * CHUNK_BYTES, p, 2 * i, hi, lo);
-            store_fb16(sq + (tc::FB_R3 + h) * FB_BYTES, ro, 16 * i, hi, lo);
+            store_fb16(sq + (tc::FB_R3 + h) * FB_BYTES, 16 * i, hi, lo);
           }
         }
         fence_before_sync();
@@ -310,7 +307,7 @@ __global__ void __launch_bounds__(k3::NT, 2)
             uint32_t hi[8], lo[8];
             split16(y, hi, lo);
             store_group16(lane_t + C_SA + 16 * gq, hi, lo);
-            store_fb16(sq + (tc::FB_O2 + (gq >> 1)) * FB_BYTES, ro, 16 * (gq & 1), hi, lo);
+            store_fb16(sq + (tc::FB_O2 + (gq >> 1)) * FB_BYTES, 16 * (gq & 1), hi, lo);
           }
           tmem_wait_st();
           fence_before_sync();
@@ -406,17 +403,10 @@ __global__ void __launch_bounds__(k3::NT, 2)
           split16(dz, zh, zl);
           unsigned char* yblk = sq + tc::FB_DY0 * FB_BYTES;
           unsigned char* zblk = sq + tc::FB_DO0 * FB_BYTES;
-          store_fb16(yblk, ro, 0, hi, lo);
-          store_fb16(zblk, ro, 0, zh, zl);
-#pragma unroll
-          for (int c = KIN; c < 32; ++c) {
-            unsigned char* ry = yblk + c * 128 + ro.o[c & 7];
-            unsigned char* rz = zblk + c * 128 + ro.o[c & 7];
-            st_half(ry, 0u);
-            st_half(reinterpret_cast<unsigned char*>(reinterpret_cast<uintptr_t>(ry) ^ 64), 0u);
-            st_half(rz, 0u);
-            st_half(reinterpret_cast<unsigned char*>(reinterpret_cast<uintptr_t>(rz) ^ 64), 0u);
-          }
+          store_fb16(yblk, 0, hi, lo);
+          store_fb16(zblk, 0, zh, zl);
+          store_fb_tail(yblk, false);
+          store_fb_tail(zblk, false);
           unsigned char* base = smem + SM_XIN + (p % 8) * 16 + (p / 8) * 128;
           *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(base + 2048) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
@@ -452,10 +442,10 @@ __global__ void __launch_bounds__(k3::NT, 2)
             uint32_t hi[8], lo[8];
             split16(v, hi, lo);
             store_group16(lane_t + C_SA + 16 * gq, hi, lo);
-            store_fb16(sq + (tc::FB_DO2 + (gq >> 1)) * FB_BYTES, ro, 16 * (gq & 1), hi, lo);
+            store_fb16(sq + (tc::FB_DO2 + (gq >> 1)) * FB_BYTES, 16 * (gq & 1), hi, lo);
             apply_bits16(v, (uint32_t)(m_y2 >> (16 * i)));
             split16(v, hi, lo);
-            store_fb16(sq + (tc::FB_DY2 + (gq >> 1)) * FB_BYTES, ro, 16 * (gq & 1), hi, lo);
+            store_fb16(sq + (tc::FB_DY2 + (gq >> 1)) * FB_BYTES, 16 * (gq & 1), hi, lo);
             const int cb = cu & 1;   // chunk i = features [32 i, 32 i + 32): group 2 i from half 0, 2 i + 1 from half 1
             mbar_wait_parked(&bars[CH_EMPTY + cb], ((cu >> 1) & 1) ^ 1);
             store_chunk16(smem + SM_CHUNK + cb * CHUNK_BYTES, p, 2 * h, hi, lo);
@@ -483,7 +473,7 @@ __global__ void __launch_bounds__(k3::NT, 2)
             uint32_t hi[8], lo[8];
             split16(v, hi, lo);
             store_chunk16(smem + SM_CHUNK + h * CHUNK_BYTES, p, 2 * i, hi, lo);
-            store_fb16(sq + (tc::FB_DZ3 + h) * FB_BYTES, ro, 16 * i, hi, lo);
+            store_fb16(sq + (tc::FB_DZ3 + h) * FB_BYTES, 16 * i, hi, lo);
           }
         }
         fence_before_sync();
@@ -507,7 +497,7 @@ __global__ void __launch_bounds__(k3::NT, 2)
             uint32_t hi[8], lo[8];
             split16(v, hi, lo);
             store_group16(lane_t + col, hi, lo);
-            store_fb16(sq + (tc::FB_DZ2 + (gq >> 1)) * FB_BYTES, ro, 16 * (gq & 1), hi, lo);
+            store_fb16(sq + (tc::FB_DZ2 + (gq >> 1)) * FB_BYTES, 16 * (gq & 1), hi, lo);
           }
           tmem_wait_st();
           fence_before_sync();

@@ -39,6 +39,9 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn, int b_
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// both shared-memory operands MN-major (bits 15 / 16): a core matrix is 8 k x (8 halfs of M or N); in the matrix
+// descriptor SBO is then the stride between groups of 8 along M / N and LBO the stride between groups of 8 along k
+__host__ __device__ constexpr uint32_t idesc_f16_mn(int M, int N) { return idesc_f16(M, N) | (1u << 15) | (1u << 16); }
 
 // ---------------------------------------------------------------- MMA issue (one thread)
 __device__ __forceinline__ void mma_ss_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {

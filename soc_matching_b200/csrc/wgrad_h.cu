@@ -2,11 +2,11 @@
 // trajectory points as the contraction index (kind::f16, three products per pair, fp32 accumulation in TMEM).
 //
 //   dW[out][in] += sum_p dY[p][out] * Act[p][in]
-// The scratch written by loss_h.cu has the geometry of loss_tc.cuh (tile -> 4 quarters -> 59 feature blocks of 32 rows x
-// 128 bytes, 16-byte chunks XOR-permuted by (feature & 7)), but a feature row holds the 32 points of the quarter as
-//     [32 x fp16 hi | 32 x fp16 lo]      of the OPERAND-SCALED value (the very hi / lo pairs K3a feeds its own MMAs),
-// i.e. it is a K-major fp16 operand of K = 64 whose first half is the hi plane and second half the lo plane: one
-// cp.async.bulk lands a run of feature blocks in shared memory ready for the MMA, and a product is
+// The scratch written by loss_h.cu keeps the block structure of loss_tc.cuh (tile -> 4 quarters -> 59 feature blocks of
+// 32 features x 4 KB), but a block holds the 32 points of the quarter as fp16 hi and lo planes of the OPERAND-SCALED value
+// (the very hi / lo pairs K3a feeds its own MMAs) in the canonical no-swizzle MN-major layout: per group of 8 features eight
+// 128-byte core matrices (8 points x 8 features), point groups 0..3 = hi, 4..7 = lo.  It is an fp16 operand of K = 64:
+// one cp.async.bulk lands a run of feature blocks in shared memory ready for the MMA, and a product is
 //     A_hi B_hi + A_lo B_hi + A_hi B_lo   =   k-steps (0,1)x(0,1), (2,3)x(0,1), (0,1)x(2,3)   of 16 points each.
 // Compared with wgrad_tc.cu (fp32 scratch) there is no in-kernel hi / lo split -- that pass and its second copy of every
 // stage made the old kernel latency-bound with two 114 KB stages -- so three 56 KB stages fit and the kernel streams the
@@ -31,7 +31,8 @@ constexpr int WH_SMEM = WH_STAGES * WG_RAW_BYTES + 1024 + 256;
 constexpr int WH_NT = 192;
 constexpr int WH_PREFETCH = 6;
 
-__device__ __forceinline__ uint64_t mn_desc_h(uint32_t saddr) { return smem_desc(saddr, 16, 1024) | DESC_SW128; }
+// MN-major, no swizzle: LBO = 128 (next 8 points), SBO = 1024 (next 8 features)
+__device__ __forceinline__ uint64_t mn_desc_h(uint32_t saddr) { return smem_desc(saddr, 128, 1024); }
 __device__ __forceinline__ void red_add_h(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
@@ -157,13 +158,13 @@ __global__ void __launch_bounds__(WH_NT, 1) wgrad_h_kernel(const unsigned char* 
               const int nm = c_stage[l].n_mma;
               for (int j = 0; j < nm; ++j) {
                 const Mma m = c_stage[l].mma[j];
-                const uint32_t idesc = idesc_f16(128, m.N);
+                const uint32_t idesc = idesc_f16_mn(128, m.N);
                 const uint32_t dcol = tm + (uint32_t)m.col;
                 const uint32_t a0 = st + m.a_off, b0 = st + m.b_off;
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {   // hi plane: bytes [0,64) of a row, lo plane: [64,128); 16 points = 32 bytes
-                  const uint64_t ah = mn_desc_h(a0 + ks * 32), al = mn_desc_h(a0 + 64 + ks * 32);
-                  const uint64_t bh = mn_desc_h(b0 + ks * 32), bl = mn_desc_h(b0 + 64 + ks * 32);
+                for (int ks = 0; ks < 2; ++ks) {   // 16 points = two core matrices = 256 bytes; lo plane 512 bytes further
+                  const uint64_t ah = mn_desc_h(a0 + ks * 256), al = mn_desc_h(a0 + 512 + ks * 256);
+                  const uint64_t bh = mn_desc_h(b0 + ks * 256), bl = mn_desc_h(b0 + 512 + ks * 256);
                   mma_ss_f16(dcol, ah, bh, idesc, (first && ks == 0) ? 0u : 1u);
                   mma_ss_f16(dcol, al, bh, idesc, 1u);
                   mma_ss_f16(dcol, ah, bl, idesc, 1u);
