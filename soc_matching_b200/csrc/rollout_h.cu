@@ -51,17 +51,17 @@ __device__ __forceinline__ void warp_max_to(uint32_t* slot, float v) {
 }
 
 // Calibration: (a) max |w| per layer (blocks 0..9), (b) max |activation| of the six calibrated layer inputs over
-// n_samples sample points evaluated in fp32 (one warp per point, unet_generic.cuh).  Sample points:
+// n_samples sample points evaluated in fp32 (one 256-thread block per point).  Sample points:
 //   rollout mode (states == nullptr): x0 of the first paths, spread by r sqrt(lmbd T) z with r in {0, 1/2, 1, 2} and
 //       Philox normal z, at t in {0, T/3, 2T/3, T} -- the scale only has to be right within ~2^10 (head room) upwards
 //       and ~2^15 downwards (precision floor), see unet_h.cuh;
 //   loss mode: points of the stored trajectories, strided over all (K+1) B of them.
-constexpr int CALIB_BWD_FLOATS = 32 + 2 * H0 + 2 * H1 + H2;
+constexpr int CALIB_BWD_FLOATS = 32 + 2 * H0 + 2 * H1 + H2 + H0;
 __global__ void __launch_bounds__(256) calib_h_kernel(socm_unet net, const float* __restrict__ wc, CalibArgs c,
                                                       uint32_t* __restrict__ mx) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* smem = reinterpret_cast<float*>(smem_raw);
-  const int d = net.d, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = net.d;
   if (blockIdx.x == 10) {  // max |w_m| over all paths (exact: the global scale of the loss gradient hangs on it)
     float v = 0.f;
     if (c.w != nullptr)
@@ -79,108 +79,167 @@ __global__ void __launch_bounds__(256) calib_h_kernel(socm_unet net, const float
     warp_max_to(mx + N_ACT + l, v);
     return;
   }
-  const int per_warp = generic::fwd_floats(d, H0, H1, H2) + CALIB_BWD_FLOATS;
-  generic::FwdBuf b = generic::carve_fwd(smem + (size_t)warp * per_warp, d, H0, H1, H2);
-  for (int i = (blockIdx.x - 11) * 8 + warp; i < c.n_samples; i += (gridDim.x - 11) * 8) {
-    if (c.states == nullptr) {
-      const int nb = c.B < 64 ? c.B : 64;
-      const int m = i % nb, v = (i / nb) & 3;
-      const float T = __ldg(c.step_tab + 4 * c.K + c.K - 1) + __ldg(c.step_tab + c.K - 1);
-      const float r = (v == 0 ? 0.f : (v == 1 ? 0.5f : (v == 2 ? 1.f : 2.f))) * sqrtf(c.lmbd * T);
-      if (lane == 0) {
-        b.xin[0] = T * (float)v / 3.f;
-        for (int blk = 0; blk * 4 < d; ++blk) {
-          float z[4];
-          // fixed key: the calibration (hence the power-of-two scales, hence every rounding) must not depend on the
-          // call's noise seed, or replaying a run with its own noise injected would not be bit-identical
-          philox_normal4(0x5bd1e995c0ffee11ull, (uint64_t)i, 0xffffu, (uint32_t)blk, z);
-          for (int j = 0; j < 4 && blk * 4 + j < d; ++j)
-            b.xin[1 + blk * 4 + j] = __ldg(c.x0 + (size_t)m * d + blk * 4 + j) + r * z[j];
-        }
-      }
-    } else {
-      const size_t n_pts = (size_t)(c.K + 1) * c.B;
-      const size_t pt = (size_t)(((double)i + 0.5) / c.n_samples * (double)n_pts);
-      const int ti = (int)(pt / c.B);
-      if (lane == 0) b.xin[0] = __ldg(c.ts + ti);
-      for (int j = lane; j < d; j += 32) b.xin[1 + j] = __ldg(c.states + pt * d + j);
+  // ---- one sample per block: thread n owns output n of a layer (forward) / input k (transposed products)
+  const int tid = threadIdx.x;
+  generic::FwdBuf b = generic::carve_fwd(smem, d, H0, H1, H2);
+  const int i = blockIdx.x - 11;
+  if (i >= c.n_samples) return;
+  size_t pt = 0;
+  int ti = 0;
+  if (c.states == nullptr) {
+    const int nb = c.B < 64 ? c.B : 64;
+    const int m = i % nb, v = (i / nb) & 3;
+    const float T = __ldg(c.step_tab + 4 * c.K + c.K - 1) + __ldg(c.step_tab + c.K - 1);
+    const float r = (v == 0 ? 0.f : (v == 1 ? 0.5f : (v == 2 ? 1.f : 2.f))) * sqrtf(c.lmbd * T);
+    if (tid == 0) b.xin[0] = T * (float)v / 3.f;
+    if (tid * 4 < d) {
+      float z[4];
+      // fixed key: the calibration (hence the power-of-two scales, hence every rounding) must not depend on the
+      // call's noise seed, or replaying a run with its own noise injected would not be bit-identical
+      philox_normal4(0x5bd1e995c0ffee11ull, (uint64_t)i, 0xffffu, (uint32_t)tid, z);
+      for (int j = 0; j < 4 && tid * 4 + j < d; ++j)
+        b.xin[1 + tid * 4 + j] = __ldg(c.x0 + (size_t)m * d + tid * 4 + j) + r * z[j];
     }
-    __syncwarp();
-    generic::forward(net, b, lane);
-    auto amax = [&](const float* v, int n, bool relu) {
-      float a = 0.f;
-      for (int k = lane; k < n; k += 32) a = fmaxf(a, relu ? v[k] : fabsf(v[k]));
-      return a;
-    };
-    warp_max_to(mx + A_X, amax(b.xin, d + 1, false));
-    warp_max_to(mx + A_R1, amax(b.r1, H0, false));
-    warp_max_to(mx + A_R2, amax(b.r2, H1, false));
-    warp_max_to(mx + A_R3, amax(b.r3, H2, false));
-    warp_max_to(mx + A_O2, amax(b.o2, H1, false));
-    warp_max_to(mx + A_Y1, amax(b.y1, H0, true));   // y1 holds the pre-ReLU values of up_1
-    __syncwarp();
-    if (c.target != nullptr && c.states != nullptr) {
-      // backward gains: max |d_layer| for the row-normalised loss gradient dv / max|dv| at this point (loss_h.cu);
-      // dv ~ nabla_V - target up to a positive factor (sigma and the warm start only turn it slightly)
-      float* bw = smem + (size_t)warp * per_warp + generic::fwd_floats(d, H0, H1, H2);
-      float* d_y0 = bw;            // [d]
-      float* d_o1 = d_y0 + 32;     // [H0]
-      float* d_o2 = d_o1 + H0;     // [H1]
-      float* d_r2 = d_o2 + H1;     // [H1]
-      float* d_r3 = d_r2 + H1;     // [H2]
-      const size_t n_pts = (size_t)(c.K + 1) * c.B;
-      const size_t pt = (size_t)(((double)i + 0.5) / c.n_samples * (double)n_pts);
-      const int ti = (int)(pt / c.B), m = (int)(pt - (size_t)ti * c.B);
-      float dvm = 0.f;
-      for (int j = lane; j < d; j += 32) {
-        const float dv = b.o0[j] - __ldg(c.target + (size_t)m * c.ldt + (size_t)ti * d + j);
-        d_y0[j] = dv;
-        dvm = fmaxf(dvm, fabsf(dv));
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) dvm = fmaxf(dvm, __shfl_xor_sync(0xffffffffu, dvm, o));
-      if (lane == 0 && dvm > 0.f) atomicMax(mx + MX_DIFF, __float_as_uint(dvm));
-      if (dvm > 0.f) {
-        __syncwarp();
-        for (int j = lane; j < d; j += 32) d_y0[j] = b.y0[j] > 0.f ? d_y0[j] / dvm : 0.f;
-        __syncwarp();
-        generic::dense_t(net.w[8], d, H0, d_y0, d_o1, false, lane);
-        __syncwarp();
-        for (int k = lane; k < H0; k += 32) d_o1[k] = b.y1[k] > 0.f ? d_o1[k] : 0.f;   // d_y1
-        __syncwarp();
-        warp_max_to(mx + MX_B + B_DY1, amax(d_o1, H0, false));
-        generic::dense_t(net.w[7], H0, H1, d_o1, d_o2, false, lane);
-        __syncwarp();
-        warp_max_to(mx + MX_B + B_DO2, amax(d_o2, H1, false));
-        generic::dense_t(net.w[5], H1, H1, d_o2, d_r2, false, lane);
-        __syncwarp();
-        for (int k = lane; k < H1; k += 32) d_o2[k] = b.y2[k] > 0.f ? d_o2[k] : 0.f;   // d_y2
-        __syncwarp();
-        generic::dense_t(net.w[6], H1, H2, d_o2, d_r3, false, lane);
-        __syncwarp();
-        for (int k = lane; k < H2; k += 32) d_r3[k] = b.r3[k] > 0.f ? d_r3[k] : 0.f;   // d_z3
-        __syncwarp();
-        warp_max_to(mx + MX_B + B_DZ3, amax(d_r3, H2, false));
-        generic::dense_t(net.w[2], H2, H1, d_r3, d_r2, true, lane);
-        __syncwarp();
-        for (int k = lane; k < H1; k += 32) d_r2[k] = b.r2[k] > 0.f ? d_r2[k] : 0.f;   // d_z2
-        __syncwarp();
-        warp_max_to(mx + MX_B + B_DZ2, amax(d_r2, H1, false));
-        // d_z1 = m_r1 . (W_d1^T d_z2 + W_r1^T d_o1),  d_o1 = W_u0^T d_y0 (recomputed: the buffer now holds d_y1)
-        float* d_r1 = bw + 32 + H0 + 2 * H1 + H2;   // [H0]
-        generic::dense_t(net.w[8], d, H0, d_y0, d_o1, false, lane);
-        __syncwarp();
-        generic::dense_t(net.w[4], H0, H0, d_o1, d_r1, false, lane);
-        __syncwarp();
-        generic::dense_t(net.w[1], H1, H0, d_r2, d_r1, true, lane);
-        __syncwarp();
-        for (int k = lane; k < H0; k += 32) d_r1[k] = b.r1[k] > 0.f ? d_r1[k] : 0.f;
-        __syncwarp();
-        warp_max_to(mx + MX_B + B_DZ1, amax(d_r1, H0, false));
-      }
-      __syncwarp();
-    }
+  } else {
+    const size_t n_pts = (size_t)(c.K + 1) * c.B;
+    pt = (size_t)(((double)i + 0.5) / c.n_samples * (double)n_pts);
+    ti = (int)(pt / c.B);
+    if (tid == 0) b.xin[0] = __ldg(c.ts + ti);
+    if (tid < d) b.xin[1 + tid] = __ldg(c.states + pt * d + tid);
   }
+  __syncthreads();
+  // out[n] = bias[n] + sum_k W[n][k] in[k]  (four partial sums: the loads of a row are independent, the chain is short)
+  auto dense = [&](int l, int nout, int nin, const float* in, float* out) {
+    for (int n = tid; n < nout; n += blockDim.x) {
+      const float* row = net.w[l] + (size_t)n * nin;
+      float a0 = __ldg(net.b[l] + n), a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int k = 0;
+      for (; k + 4 <= nin; k += 4) {
+        a0 = fmaf(__ldg(row + k), in[k], a0);
+        a1 = fmaf(__ldg(row + k + 1), in[k + 1], a1);
+        a2 = fmaf(__ldg(row + k + 2), in[k + 2], a2);
+        a3 = fmaf(__ldg(row + k + 3), in[k + 3], a3);
+      }
+      for (; k < nin; ++k) a0 = fmaf(__ldg(row + k), in[k], a0);
+      out[n] = (a0 + a1) + (a2 + a3);
+    }
+  };
+  // din[k] (+)= sum_n W[n][k] dout[n]  (coalesced over k)
+  auto dense_t = [&](int l, int nout, int nin, const float* dout, float* din, bool accumulate) {
+    for (int k = tid; k < nin; k += blockDim.x) {
+      const float* col = net.w[l] + k;
+      float a0 = accumulate ? din[k] : 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int n = 0;
+      for (; n + 4 <= nout; n += 4) {
+        a0 = fmaf(__ldg(col + (size_t)n * nin), dout[n], a0);
+        a1 = fmaf(__ldg(col + (size_t)(n + 1) * nin), dout[n + 1], a1);
+        a2 = fmaf(__ldg(col + (size_t)(n + 2) * nin), dout[n + 2], a2);
+        a3 = fmaf(__ldg(col + (size_t)(n + 3) * nin), dout[n + 3], a3);
+      }
+      for (; n < nout; ++n) a0 = fmaf(__ldg(col + (size_t)n * nin), dout[n], a0);
+      din[k] = (a0 + a1) + (a2 + a3);
+    }
+  };
+  auto relu = [&](float* v, int n) {
+    if (tid < n) v[tid] = fmaxf(v[tid], 0.f);
+  };
+  // max over the block's first n values (n <= 256 = blockDim.x)
+  auto amax_to = [&](uint32_t* slot, const float* v, int n, bool relu_v) {
+    const float a = tid < n ? (relu_v ? v[tid] : fabsf(v[tid])) : 0.f;
+    warp_max_to(slot, a);
+  };
+  // forward (models.py:202-242), as unet_generic.cuh
+  dense(0, H0, d + 1, b.xin, b.r1);
+  __syncthreads();
+  relu(b.r1, H0);
+  __syncthreads();
+  dense(1, H1, H0, b.r1, b.r2);
+  dense(4, H0, H0, b.r1, b.o1);
+  __syncthreads();
+  relu(b.r2, H1);
+  __syncthreads();
+  dense(2, H2, H1, b.r2, b.r3);
+  dense(5, H1, H1, b.r2, b.o2);
+  __syncthreads();
+  relu(b.r3, H2);
+  __syncthreads();
+  dense(6, H1, H2, b.r3, b.y2);
+  __syncthreads();
+  if (tid < H1) b.o2[tid] += fmaxf(b.y2[tid], 0.f);
+  __syncthreads();
+  dense(7, H0, H1, b.o2, b.y1);
+  __syncthreads();
+  if (tid < H0) b.o1[tid] += fmaxf(b.y1[tid], 0.f);
+  __syncthreads();
+  dense(8, d, H0, b.o1, b.y0);
+  dense(3, d, d + 1, b.xin, b.o0);
+  __syncthreads();
+  if (tid < d) b.o0[tid] += fmaxf(b.y0[tid], 0.f);
+  amax_to(mx + A_X, b.xin, d + 1, false);
+  amax_to(mx + A_R1, b.r1, H0, false);
+  amax_to(mx + A_R2, b.r2, H1, false);
+  amax_to(mx + A_R3, b.r3, H2, false);
+  amax_to(mx + A_O2, b.o2, H1, false);
+  amax_to(mx + A_Y1, b.y1, H0, true);   // y1 holds the pre-ReLU values of up_1
+  __syncthreads();
+  if (c.target == nullptr || c.states == nullptr) return;
+  // backward gains: max |d_layer| for the row-normalised loss gradient dv / max|dv| at this point (loss_h.cu);
+  // dv ~ nabla_V - target up to a positive factor (sigma and the warm start only turn it slightly)
+  float* bw = smem + generic::fwd_floats(d, H0, H1, H2);
+  float* d_y0 = bw;            // [d]; bw[31] = max |dv|
+  float* d_o1 = d_y0 + 32;     // [H0]
+  float* d_o2 = d_o1 + H0;     // [H1]
+  float* d_r2 = d_o2 + H1;     // [H1]
+  float* d_r3 = d_r2 + H1;     // [H2]
+  float* d_r1 = d_r3 + H2;     // [H0]
+  const int m = (int)(pt - (size_t)ti * c.B);
+  if (tid < 32) {
+    float dvm = 0.f;
+    for (int j = tid; j < d; j += 32) {
+      const float dv = b.o0[j] - __ldg(c.target + (size_t)m * c.ldt + (size_t)ti * d + j);
+      d_y0[j] = dv;
+      dvm = fmaxf(dvm, fabsf(dv));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dvm = fmaxf(dvm, __shfl_xor_sync(0xffffffffu, dvm, o));
+    if (tid == 0) {
+      if (dvm > 0.f) atomicMax(mx + MX_DIFF, __float_as_uint(dvm));
+      bw[31] = dvm;
+    }
+    __syncwarp();
+    for (int j = tid; j < d; j += 32) d_y0[j] = (dvm > 0.f && b.y0[j] > 0.f) ? d_y0[j] / dvm : 0.f;
+  }
+  __syncthreads();
+  if (!(bw[31] > 0.f)) return;
+  dense_t(8, d, H0, d_y0, d_o1, false);   // d_o1 = W_u0^T d_y0
+  __syncthreads();
+  dense_t(4, H0, H0, d_o1, d_r1, false);  // W_r1^T d_o1 (kept for d_z1)
+  __syncthreads();
+  if (tid < H0) d_o1[tid] = b.y1[tid] > 0.f ? d_o1[tid] : 0.f;   // d_y1
+  __syncthreads();
+  amax_to(mx + MX_B + B_DY1, d_o1, H0, false);
+  dense_t(7, H0, H1, d_o1, d_o2, false);
+  __syncthreads();
+  amax_to(mx + MX_B + B_DO2, d_o2, H1, false);
+  dense_t(5, H1, H1, d_o2, d_r2, false);
+  __syncthreads();
+  if (tid < H1) d_o2[tid] = b.y2[tid] > 0.f ? d_o2[tid] : 0.f;   // d_y2
+  __syncthreads();
+  dense_t(6, H1, H2, d_o2, d_r3, false);
+  __syncthreads();
+  if (tid < H2) d_r3[tid] = b.r3[tid] > 0.f ? d_r3[tid] : 0.f;   // d_z3
+  __syncthreads();
+  amax_to(mx + MX_B + B_DZ3, d_r3, H2, false);
+  dense_t(2, H2, H1, d_r3, d_r2, true);
+  __syncthreads();
+  if (tid < H1) d_r2[tid] = b.r2[tid] > 0.f ? d_r2[tid] : 0.f;   // d_z2
+  __syncthreads();
+  amax_to(mx + MX_B + B_DZ2, d_r2, H1, false);
+  dense_t(1, H1, H0, d_r2, d_r1, true);   // d_z1 = m_r1 . (W_d1^T d_z2 + W_r1^T d_o1)
+  __syncthreads();
+  if (tid < H0) d_r1[tid] = b.r1[tid] > 0.f ? d_r1[tid] : 0.f;
+  __syncthreads();
+  amax_to(mx + MX_B + B_DZ1, d_r1, H0, false);
 }
 
 // Scales (every thread recomputes them from the max buffer: a few dozen flops).  sw: weight scales (WScale), sa: forward
@@ -288,9 +347,8 @@ int setup_h(const socm_unet* net, unsigned char* ws, const CalibArgs& c, bool wi
   SOCM_CUDA(cudaMemsetAsync(mx, 0, 64 * sizeof(uint32_t), stream));
   fold_h_kernel<<<NY, H0, 0, stream>>>(*net, wc, small);
   SOCM_LAUNCH_CHECK();
-  const size_t smem = 8 * (size_t)(generic::fwd_floats(net->d, H0, H1, H2) + CALIB_BWD_FLOATS) * sizeof(float);
-  SOCM_CUDA(cudaFuncSetAttribute(calib_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  calib_h_kernel<<<11 + (c.n_samples + 7) / 8, 256, smem, stream>>>(*net, wc, c, mx);
+  const size_t smem = (size_t)(generic::fwd_floats(net->d, H0, H1, H2) + CALIB_BWD_FLOATS) * sizeof(float);
+  calib_h_kernel<<<11 + c.n_samples, 256, smem, stream>>>(*net, wc, c, mx);
   SOCM_LAUNCH_CHECK();
   pack_h_kernel<<<96, 256, 0, stream>>>(*net, wc, mx, ws, small, with_bwd ? 1 : 0, c.loss_scale);
   SOCM_LAUNCH_CHECK();
