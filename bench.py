@@ -172,7 +172,7 @@ def kernel_source_hash():
     """sha256 over the K3 kernel sources: a committed ncu traffic figure is only reported while it still describes
     the kernels that are being timed."""
     h = hashlib.sha256()
-    for f in ("loss_tc.cu", "wgrad_tc.cu", "unet_tc.cuh", "loss_tc.cuh"):
+    for f in ("loss_h.cu", "wgrad_h.cu", "unet_h.cuh", "loss_tc.cuh", "wgrad_tables.cuh", "umma.cuh"):
         with open(os.path.join(ROOT, "soc_matching_b200", "csrc", f), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()[:16]
@@ -296,8 +296,9 @@ def gpu_arm(args):
         return
     # ---- rooflines (rank 0's shard).  achieved = ALGORITHMIC fp32 FLOP of all launches of the timed region / the sum
     # of their CUDA-event times; peak = measured dense bf16 GEMM (sustained: the kernels run inside a long step).
-    # The kernels issue kind::tf32 MMAs three times per product (3xTF32, fp32-class accuracy), so the ceiling of this
-    # arithmetic is the measured tf32 rate / 3; both fractions are reported.
+    # Every product of the UNet kernels is three tensor-core MMAs (fp32-class accuracy): fp16 hi/lo splits on kind::f16
+    # (the engine this workload runs, csrc/unet_h.cuh) or 3xTF32 (csrc/unet_tc.cuh; K2 always), so the ceiling of the
+    # executed arithmetic is the measured dense rate of that kind / 3; both fractions are reported.
     n_local = hi - lo
     points = (K + 1) * n_local * args.steps
     tensor_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
@@ -324,33 +325,43 @@ def gpu_arm(args):
     def frac(x, scale=1.0):
         return None if x is None else round(x * scale / tensor_peak, 4)
 
-    def ceil_frac(x, ex_ratio):
-        return None if x is None else round(x * ex_ratio / (TF32_MEASURED / 3.0), 4)
+    # engine of the UNet kernels, as csrc/loss.cu:95 and csrc/rollout.cu:277 choose it (fp16 split wherever the default
+    # architecture with d <= 15 runs on the tensor cores, unless SOCM_F16=0 / simulate.ENGINE say otherwise)
+    f16 = d <= 15 and os.environ.get("SOCM_F16") != "0" and sb.simulate.ENGINE != "tf32"
+    unet_ceiling = tensor_peak / 3.0 if f16 else TF32_MEASURED / 3.0
+    eng = "3 x kind::f16 on fp16 hi/lo splits" if f16 else "3xTF32"
+    sfx = "h" if f16 else "tc"
+
+    def ceil_frac(x, ex_ratio, ceiling=None):
+        return None if x is None else round(x * ex_ratio / (ceiling or unet_ceiling), 4)
 
     rnd = lambda x: None if x is None else round(x, 2)  # noqa: E731
     roofline = {
-        "kernel": "K3: loss_tc_kernel + wgrad_tc_kernel (tcgen05, 3xTF32)", "bound": "tensor",
+        "kernel": f"K3: loss_{sfx}_kernel + wgrad_{sfx}_kernel (tcgen05, {eng})", "bound": "tensor",
         "achieved": rnd(k3), "peak": tensor_peak, "unit": "TFLOP/s", "frac": frac(k3),
         "traffic": traffic, "traffic_source": traffic_src, "peak_source": f"{peak_src} bf16_tflops_sustained",
         "executed_tflops": rnd(k3 * fm["ex_k3"] / fm["k3"]) if k3 else None,
-        "frac_of_3xtf32_ceiling": ceil_frac(k3, fm["ex_k3"] / fm["k3"]),
+        "frac_of_3mma_ceiling": ceil_frac(k3, fm["ex_k3"] / fm["k3"]),
+        "ceiling_3mma_tflops": round(unet_ceiling, 1),
         "note": "achieved = ALGORITHMIC fp32 FLOP of the reference's network (SURVEY.md 8d) summed over all launches of "
                 "the timed region / summed CUDA-event time; the kernels issue fewer (executed_tflops): res_1 is folded "
-                "into up_0 algebraically (DESIGN.md 3.1).  Every product is 3 kind::tf32 MMAs, so the ceiling of the "
-                f"executed arithmetic is the measured dense tf32 rate ({TF32_MEASURED:.0f} TFLOP/s, "
-                "profiles/r1_umma_probe.log) / 3",
+                "into up_0 algebraically (DESIGN.md 3.1).  Every product is 3 MMAs, so the ceiling of the executed "
+                "arithmetic is a third of the dense rate of the MMA kind: " +
+                ("the measured bf16/fp16 peak above (kind::f16 issues at the bf16 rate, profiles/r2_f16_probe.log)" if f16
+                 else f"the measured dense tf32 rate ({TF32_MEASURED:.0f} TFLOP/s, profiles/r1_umma_probe.log)") +
+                ".  K3a + K3b together are bounded by the HBM traffic of the activation scratch (traffic, DESIGN.md 3.4)",
         "algorithmic_flop_per_launch": fm["k3"] * (K + 1) * chunk,
         "launch_ms_sum": round(kernel_ms_sum.get("loss_fwdbwd", float("nan")), 3),
         "kernel_share_of_step": round(kernel_ms_sum.get("loss_fwdbwd", 0.0) / args.steps / ms_per_step, 3),
-        "rollout": {"kernel": "rollout_tc_kernel (tcgen05, 3xTF32)", "achieved_tflops": rnd(k1), "frac": frac(k1),
-                    "frac_of_3xtf32_ceiling": ceil_frac(k1, fm["ex_fwd"] / fm["fwd"]),
+        "rollout": {"kernel": f"rollout_{sfx}_kernel (tcgen05, {eng})", "achieved_tflops": rnd(k1), "frac": frac(k1),
+                    "frac_of_3mma_ceiling": ceil_frac(k1, fm["ex_fwd"] / fm["fwd"]),
                     "hbm_gbs": rnd(n_local * K * args.steps * (12 * d + 8) / (kernel_ms_sum["rollout"] * 1e-3) / 1e9),
                     "hbm_frac": round(n_local * K * args.steps * (12 * d + 8) / (kernel_ms_sum["rollout"] * 1e-3) / 1e9
                                       / float(peaks["hbm_gbs"]), 4),
                     "share_of_step": round(kernel_ms_sum["rollout"] / args.steps / ms_per_step, 3)},
         "target": {"kernel": "target_tc_kernel / target_bwd_tc_kernel (tcgen05, 3xTF32; grouped SIMT with stopping times)",
-                   "fwd_tflops": rnd(k2f), "fwd_frac": frac(k2f), "fwd_frac_of_3xtf32_ceiling": ceil_frac(k2f, 1.0),
-                   "bwd_tflops": rnd(k2b), "bwd_frac": frac(k2b), "bwd_frac_of_3xtf32_ceiling": ceil_frac(k2b, 1.0),
+                   "fwd_tflops": rnd(k2f), "fwd_frac": frac(k2f), "fwd_frac_of_3xtf32_ceiling": ceil_frac(k2f, 1.0, TF32_MEASURED / 3.0),
+                   "bwd_tflops": rnd(k2b), "bwd_frac": frac(k2b), "bwd_frac_of_3xtf32_ceiling": ceil_frac(k2b, 1.0, TF32_MEASURED / 3.0),
                    "share_of_step": round((kernel_ms_sum.get("target", 0.0) + kernel_ms_sum.get("target_bwd", 0.0))
                                           / args.steps / ms_per_step, 3)},
     }
@@ -362,7 +373,7 @@ def gpu_arm(args):
         "config": {"workload": workload_name(cfg) + " SOCM (rollout + target + loss + backward)", "name": args.config,
                    "global_batch": B, "paths_per_gpu": n_local, "chunk_paths": chunk, "hdims": [256, 128, 64],
                    "hdims_M": list(cfg["hdims_M"]), "noise": "in-kernel Philox4x32-10",
-                   "arithmetic": "fp32 (UNet GEMMs as 3xTF32 on tcgen05)",
+                   "arithmetic": f"fp32 (UNet GEMMs on tcgen05 as {eng}, fp32 accumulation; K2 as 3xTF32)",
                    "l2": "working set per step (GBs of trajectories) is far larger than the 126 MB L2"},
         "socm_iters_per_s": 1e3 / ms_per_step,
         "kernel_ms_per_step": {k: round(v / args.steps, 3) for k, v in kernel_ms_sum.items()},

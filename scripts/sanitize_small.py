@@ -1,5 +1,5 @@
 """Small-shape driver for compute-sanitizer: one pass through every kernel family of the path --
-tcgen05 rollout / target GEMMs / K3, FFMA tile kernels, the grouped stopping-time target, the tabulated-control
+tcgen05 rollout / target GEMMs / K3 on both engines (fp16 split, 3xTF32), FFMA tile kernels, the grouped stopping-time target, the tabulated-control
 rollout, fused Adam and the EMA statistics.
     compute-sanitizer --tool memcheck  python scripts/sanitize_small.py
     compute-sanitizer --tool racecheck python scripts/sanitize_small.py"""
@@ -13,8 +13,11 @@ import soc_matching_b200 as sb
 DEV = "cuda"
 hd = [256, 128, 64]
 gam = {"gamma": torch.tensor([2.0]), "gamma2": torch.tensor([1.0]), "gamma3": torch.tensor([1.0])}
-for kind, d, K, B, stopping, flags in [("double_well", 10, 40, 130, False, ("tc",)), ("double_well", 10, 40, 130, False, ("ffma",)),
+from soc_matching_b200 import simulate
+for kind, d, K, B, stopping, flags in [("double_well", 10, 40, 130, False, ("tc", "f16")), ("double_well", 10, 40, 130, False, ("tc", "tf32")),
+                                       ("double_well", 10, 40, 130, False, ("ffma",)),
                                        ("ou_quadratic", 20, 4, 70, False, ("tc",)), ("molecular_dynamics", 1, 12, 140, True, ("tc",))]:
+    simulate.ENGINE = "f16" if "f16" in flags else ("tf32" if "tf32" in flags else None)
     st = random_setting(kind, d, seed=1)
     hm = [64, 64] if stopping else [128, 128]
     sde = make_product_sde(st, seeded_unet(d, hd, 1), seeded_mnet(d, hm, 2, 0.1, 3 if stopping else 2), gam, hd, hm, DEV,
@@ -33,6 +36,7 @@ for kind, d, K, B, stopping, flags in [("double_well", 10, 40, 130, False, ("tc"
         out = solver.loss(B, algorithm=algo)
         out[0].backward()
     torch.cuda.synchronize()
+simulate.ENGINE = None
 # tabulated control
 st = random_setting("ou_quadratic", 6, seed=5)
 sde = make_product_sde(st, seeded_unet(6, [16, 8, 8], 1), seeded_mnet(6, [8, 8], 2), gam, [16, 8, 8], [8, 8], DEV)

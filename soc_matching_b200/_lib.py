@@ -91,6 +91,7 @@ PROTOTYPES = {
 DEBUG_PROTOTYPES = {
     "socm_debug_wgrad_tc": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
     "socm_debug_wgrad_tile_bytes": (_i64, []),
+    "socm_debug_wgrad_h": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp]),
 }
 
 ROLLOUT_FORCE_GENERIC = 1
