@@ -108,7 +108,7 @@ class SOC_Solver(nn.Module):
 
     def _k3_launches(self, udesc, nb, K):
         """Kernels one socm_unet_loss_fwdbwd_f32 call launches (csrc/loss.cu, loss_tc.cu): the tcgen05 path
-        packs the weight tapes once and runs K3a + K3b per sub-chunk of 8192 tiles; the FFMA tile path is
+        packs the weight tapes once and runs K3a + K3b per sub-launch of the scratch (16384 / 8192 tiles); the FFMA tile path is
         pack + kernel + gradient reduction; the generic path one kernel."""
         default_arch = (udesc.h0, udesc.h1, udesc.h2) == (256, 128, 64)
         if self.force_generic or not default_arch:
@@ -123,8 +123,10 @@ class SOC_Solver(nn.Module):
         _lib.check(_lib.load().socm_device_info(ctypes.byref(sms), None))
         n_sm = max(int(sms.value), 1)
         f16 = udesc.d <= 15 and simulate.ENGINE != "tf32" and os.environ.get("SOCM_F16", "1") != "0"
-        if f16:   # csrc/loss_h.cu: fold + calibration + pack, (K3a + K3b) per sub-launch of 8192 // (2 SMs) * (2 SMs) tiles, fold_finish
-            sub = (8192 // (2 * n_sm)) * (2 * n_sm)
+        if f16:   # csrc/loss_h.cu: fold + calibration + pack, (K3a + K3b) per sub-launch of 16384 // (2 SMs) * (2 SMs) tiles, fold_finish
+            env = os.environ.get("SOCM_SUB_TILES")
+            cap = int(env) if env is not None and env.isdigit() and int(env) >= 1024 else 16384   # loss_h.cu sub_tiles_cap()
+            sub = (cap // (2 * n_sm)) * (2 * n_sm)
             return 4 + 2 * ((n_tiles + sub - 1) // sub)
         # csrc/loss_tc.cu: fold + pack, (K3a + K3b) per sub-launch, fold_finish
         sub = (8192 // n_sm) * n_sm
