@@ -3,6 +3,7 @@ Monte-Carlo evaluators that loop it (utils.py:131-231), on the fused CUDA rollou
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -122,7 +123,7 @@ def rollout(sde, x0: torch.Tensor, t: torch.Tensor, lmbd: float, *, noises: Opti
         # kernels of one call: tcgen05 path = fold + pack + rollout, FFMA tile path = pack + rollout, generic = 1
         default_arch = (udesc.h0, udesc.h1, udesc.h2) == (256, 128, 64)
         n_k = 1 if (force_generic or not default_arch) else (2 if (force_ffma or udesc.d > 23) else 3)
-        if n_k == 3 and udesc.d <= 15 and ENGINE != "tf32" and (ENGINE == "f16" or (B + 127) // 128 > 148):
+        if n_k == 3 and udesc.d <= 15 and ENGINE != "tf32" and os.environ.get("SOCM_F16") != "0":
             n_k = 4   # fp16-split engine: fold + calibration + pack + rollout
         timer("rollout", n_k, lib.socm_rollout_f32, *args)
     else:
