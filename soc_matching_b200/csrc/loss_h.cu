@@ -67,7 +67,13 @@ __host__ __device__ inline int loss_h_smem_bytes() { return k3::SM_SMALL + small
 // scratch needs one 2-byte store per value: ~8x the LSU wavefronts, which bounded this kernel.)
 __device__ __forceinline__ int row_off(int r) { return r * 16; }
 __device__ __forceinline__ void st_q(unsigned char* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+#if defined(SOCM_SCRATCH_ST) && SOCM_SCRATCH_ST == 1
+  *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
+#elif defined(SOCM_SCRATCH_ST) && SOCM_SCRATCH_ST == 2
+  asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+#else
   __stcs(reinterpret_cast<uint4*>(p), make_uint4(a, b, c, d));
+#endif
 }
 // features [f0, f0 + 16) of the feature block at `blk` (already offset by row_off) from the packed pairs
 // hi[i] / lo[i] = features (f0 + 2 i, f0 + 2 i + 1); f0 a multiple of 16

@@ -170,6 +170,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // instead of returning to a software spin loop after the short default.  With two CTAs per SM the spinning warps
 // (MMA issuer, tape producer, epilogue warps between phases) otherwise take ~40 % of all issue slots away from the
 // warps that have work (ncu, first fp16 rollout kernel: BRA + SYNCS + YIELD = 39 % of executed instructions).
+#ifndef SOCM_PARK_NS
+#define SOCM_PARK_NS 100000   // suspend-time hint of the parked waits (ns)
+#endif
 __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   do {
@@ -178,7 +181,7 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity)
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_addr(bar)), "r"(parity), "r"(100000u)
+        : "r"(smem_addr(bar)), "r"(parity), "r"((uint32_t)SOCM_PARK_NS)
         : "memory");
   } while (ok == 0);
 }

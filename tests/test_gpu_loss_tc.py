@@ -42,6 +42,19 @@ def unet64(P, tx):
 
 @pytest.mark.parametrize("d,K,B", [(10, 40, 300), (1, 30, 129), (20, 9, 200)])
 def test_k3_tc_matches_fp64_autograd_away_from_kinks(d, K, B, engine):
+    _k3_vs_fp64(d, K, B, engine)
+
+
+@pytest.mark.parametrize("x_scale,t_scale,w_sigma", [(30.0, 1.0, 0.3), (0.03, 1.0, 0.3), (1.0, 1e3, 0.3), (1.0, 1e-4, 0.3),
+                                                      (1.0, 1.0, 3.0), (1.0, 1.0, None)])
+def test_k3_tc_dynamic_range(x_scale, t_scale, w_sigma, engine):
+    """The fp16-split engine scales every operand by calibrated powers of two: states far from / close to the origin,
+    targets (hence loss gradients) three orders of magnitude up and four down, importance weights spread over e^{+-9},
+    and all-zero weights (w_sigma None: loss and every gradient exactly zero, nothing non-finite)."""
+    _k3_vs_fp64(10, 20, 200, engine, x_scale, t_scale, w_sigma)
+
+
+def _k3_vs_fp64(d, K, B, engine, x_scale=1.0, t_scale=1.0, w_sigma=0.3):
     from soc_matching_b200 import _lib, networks
     lib = _lib.load()
     p = {k: v.to(DEV) for k, v in seeded_unet(d, [256, 128, 64], 31 + d).items()}
@@ -51,7 +64,7 @@ def test_k3_tc_matches_fp64_autograd_away_from_kinks(d, K, B, engine):
     g = torch.Generator(DEV).manual_seed(d)
     ts = torch.linspace(0, 1, K + 1, device=DEV)
     P = {k: v.double().requires_grad_(True) for k, v in p.items()}
-    states = torch.randn(K + 1, B, d, device=DEV, generator=g)
+    states = x_scale * torch.randn(K + 1, B, d, device=DEV, generator=g)
     for _ in range(20):   # move every point that sits within 1e-4 of a ReLU kink
         tx = torch.cat([ts.reshape(-1, 1, 1).expand(K + 1, B, 1), states], -1).double()
         with torch.no_grad():
@@ -59,11 +72,12 @@ def test_k3_tc_matches_fp64_autograd_away_from_kinks(d, K, B, engine):
         near = torch.stack([(z.abs() < 1e-4).any(-1) for z in pre]).any(0)
         if not bool(near.any()):
             break
-        states[near] = torch.randn(int(near.sum()), d, device=DEV, generator=g)
+        states[near] = x_scale * torch.randn(int(near.sum()), d, device=DEV, generator=g)
     assert not bool(near.any())
     ldt = ((K + 1) * d + 3) // 4 * 4
-    target = torch.randn(B, ldt, device=DEV, generator=g)
-    w = torch.exp(0.3 * torch.randn(B, device=DEV, generator=g))
+    target = t_scale * torch.randn(B, ldt, device=DEV, generator=g)
+    w = (torch.exp(w_sigma * torch.randn(B, device=DEV, generator=g)) if w_sigma is not None
+         else torch.zeros(B, device=DEV))
     G = torch.zeros(B, ldt, device=DEV)
     grad = torch.zeros(int(lib.socm_unet_param_count(udesc)), device=DEV)
     loss = torch.zeros(1, device=DEV, dtype=torch.float64)
@@ -79,6 +93,9 @@ def test_k3_tc_matches_fp64_autograd_away_from_kinks(d, K, B, engine):
                                              _lib.LOSS_FORCE_TC | (_lib.LOSS_F16 if engine == "f16" else _lib.LOSS_TF32),
                                              _lib.stream_ptr()))
     torch.cuda.synchronize()
+    if w_sigma is None:
+        assert float(loss) == 0.0 and float(grad.abs().max()) == 0.0 and float(G.abs().max()) == 0.0
+        return
     tx = torch.cat([ts.reshape(-1, 1, 1).expand(K + 1, B, 1), states], -1).double()
     out, _ = unet64(P, tx)
     out.retain_grad()
