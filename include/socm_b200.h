@@ -82,6 +82,10 @@ int socm_abi_version(void);
 const char* socm_last_error(void);
 /* SM count / opt-in shared memory of the current device (used to size persistent grids). */
 int socm_device_info(int* sm_count, int* smem_optin_bytes);
+/* Tensor-core engine of the default-width kernels where the call has no flag for it (the target GEMMs) and the default of
+ * the others: -1 = the SOCM_F16 environment variable, else fp16 hi/lo split on kind::f16 wherever it applies;
+ * 0 = 3xTF32; 1 = fp16 split.  Process-wide; the soc_matching_b200.simulate.ENGINE switch of the Python mirror sets it. */
+int socm_set_default_engine(int32_t engine);
 
 /* --- K1: Euler-Maruyama rollout  (replaces utils.stochastic_trajectories, utils.py:17-128,
  *     including NeuralSDE.control, method.py:58-80) ------------------------------------- */
@@ -154,7 +158,8 @@ int socm_target_prep_f32(const socm_setting* st, const float* states, const floa
  * (zero for j < i: only K-blocks with j >= i are read). */
 int socm_target_gemm_f32(const float* L, const float* R, int32_t B, int32_t K, int32_t d,
                          int32_t ldr, float* target, int32_t ldt, void* stream);
-/* The same contraction on the tcgen05 tensor cores (3xTF32, fp32 accumulation; csrc/target_tc.cu).
+/* The same contraction on the tcgen05 tensor cores, fp32 accumulation: fp16 hi/lo split on kind::f16 (csrc/target_h.cu,
+ * default) or 3xTF32 (csrc/target_tc.cu), see socm_set_default_engine.
  * workspace: socm_target_gemm_tc_workspace_bytes(K, d) bytes (hi/lo split tape of L, rebuilt every call). */
 int64_t socm_target_gemm_tc_workspace_bytes(int32_t K, int32_t d);
 int socm_target_gemm_tc_f32(const float* L, const float* R, int32_t B, int32_t K, int32_t d, int32_t ldr,
@@ -162,8 +167,11 @@ int socm_target_gemm_tc_f32(const float* L, const float* R, int32_t B, int32_t K
 /* dL[(K+1)d][ldr] (+)= G^T R  (contraction over paths), only the j >= i blocks are written. */
 int socm_target_gemm_bwd_f32(const float* G, const float* R, int32_t B, int32_t K, int32_t d,
                              int32_t ldr, int32_t ldt, float* dL, int32_t accumulate, void* stream);
-/* The same on the tcgen05 tensor cores (3xTF32; csrc/target_bwd_tc.cu).  workspace:
- * socm_target_gemm_bwd_tc_workspace_bytes(B, K, d) bytes (transposed operand scratch). */
+/* The same on the tcgen05 tensor cores: fp16 hi/lo planes on kind::f16 (csrc/target_bwd_h.cu, default) or 3xTF32
+ * (csrc/target_bwd_tc.cu).  workspace: socm_target_gemm_bwd_tc_workspace_bytes(B, K, d) bytes (operand scratch).
+ * `accumulate` is a bit field here: bit 0 = add into dL, SOCM_TARGET_BWD_TF32 / _F16 force an engine. */
+#define SOCM_TARGET_BWD_TF32 2
+#define SOCM_TARGET_BWD_F16 4
 int64_t socm_target_gemm_bwd_tc_workspace_bytes(int32_t B, int32_t K, int32_t d);
 int socm_target_gemm_bwd_tc_f32(const float* G, const float* R, int32_t B, int32_t K, int32_t d, int32_t ldr,
                                 int32_t ldt, float* dL, int32_t accumulate, void* workspace, void* stream);

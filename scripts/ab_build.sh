@@ -7,10 +7,12 @@ cd "$(dirname "$0")/.."
 NAME=$1; EXTRA=$2
 OBJ=ab/obj_$NAME; mkdir -p $OBJ
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -diag-suppress 1886"
-for f in loss_h rollout_h wgrad_h; do
+FILES=${FILES:-"loss_h rollout_h wgrad_h"}
+for f in $FILES; do
   nvcc $FLAGS $EXTRA -c soc_matching_b200/csrc/$f.cu -o $OBJ/$f.o &
 done
 wait
-OTHERS=$(ls soc_matching_b200/build/*.o | grep -v "/loss_h.o\|/rollout_h.o\|/wgrad_h.o")
+PAT=$(for f in $FILES; do echo -n "/$f.o\|"; done); PAT=${PAT%\\|}
+OTHERS=$(ls soc_matching_b200/build/*.o | grep -v "$PAT")
 nvcc -shared -o ab/lib_$NAME.so $OBJ/*.o $OTHERS -gencode arch=compute_100a,code=sm_100a
 echo ab/lib_$NAME.so

@@ -52,6 +52,20 @@ if os.environ.get("AB_K2", "1") == "1":
     t2 = timeit(lambda: _lib.check(lib.socm_target_gemm_bwd_tc_f32(G2.data_ptr(), R2.data_ptr(), B2, K, d, ldr, ldt,
                                                                     dL.data_ptr(), 1, wsb.data_ptr(), _lib.stream_ptr())), 3)
     print(f"  K2b {t2:.2f} ms for {B2} paths", end="")
+if os.environ.get("AB_K2F", "0") == "1":
+    B2 = 75776
+    ldr = ((2 * K + 1) * d + 3) // 4 * 4
+    nrows = (K + 1) * d
+    Lm = torch.randn(nrows, ldr, device=DEV, generator=g)
+    i_of_row = torch.arange(nrows, device=DEV) // d
+    col = torch.arange(ldr, device=DEV)
+    Lm[(col[None, :] < 2 * i_of_row[:, None] * d) | (col[None, :] >= (2 * K + 1) * d)] = 0.0
+    R2 = torch.randn(B2, ldr, device=DEV, generator=g)
+    T2 = torch.empty(B2, ldt, device=DEV)
+    wsf = torch.empty(int(lib.socm_target_gemm_tc_workspace_bytes(K, d)), device=DEV, dtype=torch.uint8)
+    t2f = timeit(lambda: _lib.check(lib.socm_target_gemm_tc_f32(Lm.data_ptr(), R2.data_ptr(), B2, K, d, ldr, T2.data_ptr(), ldt,
+                                                                wsf.data_ptr(), _lib.stream_ptr())), 3)
+    print(f"  K2f {t2f:.2f} ms for {B2} paths", end="")
 if os.environ.get("AB_K1", "1") == "1":
     from helpers import make_product_sde, random_setting, seeded_mnet
     stg = random_setting("double_well", d, seed=3)

@@ -60,6 +60,7 @@ PROTOTYPES = {
     "socm_abi_version": (C.c_int, []),
     "socm_last_error": (C.c_char_p, []),
     "socm_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "socm_set_default_engine": (C.c_int, [_i32]),
     "socm_rollout_workspace_bytes": (_i64, [C.POINTER(UNet)]),
     "socm_rollout_f32": (C.c_int, [C.POINTER(Setting), C.POINTER(UNet), C.POINTER(WarmTable), _vp, _vp, _vp,
                                    _u64, _u64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
@@ -105,6 +106,7 @@ LOSS_FORCE_FFMA = 2
 LOSS_FORCE_TC = 4
 LOSS_F16 = 8
 LOSS_TF32 = 16
+TARGET_BWD_TF32, TARGET_BWD_F16 = 2, 4
 
 _lib = None
 

@@ -1,5 +1,6 @@
 // api.cu -- bookkeeping entry points of the C ABI (include/socm_b200.h) and shared host helpers.
 #include <stdarg.h>
+#include <atomic>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -51,7 +52,11 @@ int validate_unet(const socm_unet* net, int d) {
 
 bool is_default_arch(const socm_unet* net) { return net->h0 == 256 && net->h1 == 128 && net->h2 == 64; }
 
+static std::atomic<int> g_engine_override{-1};
+
 int f16_default() {
+  const int o = g_engine_override.load(std::memory_order_relaxed);
+  if (o >= 0) return o;
   static const int v = [] {
     const char* e = getenv("SOCM_F16");
     return e == nullptr ? -1 : (e[0] == '1' ? 1 : 0);
@@ -95,3 +100,9 @@ int64_t socm_unet_param_count(const socm_unet* net) {
 }
 
 }  // extern "C"
+
+extern "C" int socm_set_default_engine(int32_t engine) {
+  SOCM_CHECK_ARG(engine >= -1 && engine <= 1, "engine must be -1 (environment / default), 0 (3xTF32) or 1 (fp16 split)");
+  socm::g_engine_override.store(engine, std::memory_order_relaxed);
+  return SOCM_OK;
+}

@@ -25,8 +25,15 @@ namespace hx {
 bool rollout_h_supported(const socm_unet* net);
 int64_t rollout_h_workspace_bytes();
 int launch_rollout_h(const RolloutArgs& a, const socm_unet* net, void* workspace, cudaStream_t stream);
-// K3a on the same engine (loss_h.cu); K3b stays wgrad_tc.cu
+// K3a / K3b on the same engine (loss_h.cu, wgrad_h.cu)
 bool loss_h_supported(const socm_unet* net);
 int64_t loss_h_workspace_bytes(int B, int K);
+// K2 forward on kind::f16 (target_h.cu); workspace of socm_target_gemm_tc_workspace_bytes
+int64_t target_h_workspace_bytes(int K, int d);
+int launch_target_h(const float* L, const float* R, int B, int K, int d, int ldr, float* target, int ldt, void* workspace,
+                    cudaStream_t stream);
+// K2 backward on kind::f16 (target_bwd_h.cu); workspace of socm_target_gemm_bwd_tc_workspace_bytes
+int launch_target_bwd_h(const float* G, const float* R, int B, int K, int d, int ldr, int ldt, float* dL, void* workspace,
+                        cudaStream_t stream);
 }  // namespace hx
 }  // namespace socm

@@ -246,8 +246,12 @@ extern "C" int socm_target_gemm_bwd_tc_f32(const float* G, const float* R, int32
   SOCM_CHECK_ARG(d >= 1 && d <= SOCM_MAX_DIM && K >= 1, "bad sizes");
   SOCM_CHECK_ARG(ldr >= (2 * K + 1) * d && ldt >= (K + 1) * d, "bad pitches ldr=%d ldt=%d", ldr, ldt);
   const tc::K2bGeom g = k2b_geom(B, K, d);
-  if (!accumulate) SOCM_CUDA(cudaMemsetAsync(dL, 0, (size_t)g.nrows * ldr * sizeof(float), stream));
+  if (!(accumulate & 1)) SOCM_CUDA(cudaMemsetAsync(dL, 0, (size_t)g.nrows * ldr * sizeof(float), stream));
   if (B == 0) return SOCM_OK;
+  // engine: fp16 hi / lo planes on kind::f16 (target_bwd_h.cu) unless SOCM_TARGET_BWD_TF32 or SOCM_F16=0 ask for 3xTF32
+  const bool want_f16 = (accumulate & SOCM_TARGET_BWD_F16) || (f16_default() != 0 && !(accumulate & SOCM_TARGET_BWD_TF32));
+  if (want_f16 && ldr % 4 == 0 && ldt % 4 == 0)
+    return hx::launch_target_bwd_h(G, R, B, K, d, ldr, ldt, dL, workspace, stream);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   ws += (1024 - (reinterpret_cast<uintptr_t>(ws) & 1023)) & 1023;
   const int64_t qbytes = tc::k2b_quarter_bytes(g);

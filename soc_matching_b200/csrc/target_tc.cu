@@ -241,7 +241,9 @@ extern "C" int64_t socm_target_gemm_tc_workspace_bytes(int32_t K, int32_t d) {
   // same bound as socm_target_gemm_tc_f32: make_plan fills fixed-size tables (K2_MAX_BLOCKS row blocks)
   if (((K + 1) * d + tc::K2_NB - 1) / tc::K2_NB > tc::K2_MAX_BLOCKS) return -1;
   const tc::K2Plan p = tc::make_plan((K + 1) * d, (2 * K + 1) * d, d);
-  return (int64_t)p.slot_begin[p.n_blocks] * tc::MAIN_BYTES + 1024;
+  const int64_t tcb = (int64_t)p.slot_begin[p.n_blocks] * tc::MAIN_BYTES + 1024;
+  const int64_t hb = hx::target_h_workspace_bytes(K, d);   // the fp16 tape has half as many slots
+  return tcb > hb ? tcb : hb;
 }
 
 extern "C" int socm_target_gemm_tc_f32(const float* L, const float* R, int32_t B, int32_t K, int32_t d, int32_t ldr,
@@ -253,6 +255,7 @@ extern "C" int socm_target_gemm_tc_f32(const float* L, const float* R, int32_t B
   const int nrows = (K + 1) * d, kdim = (2 * K + 1) * d;
   SOCM_CHECK_ARG((nrows + tc::K2_NB - 1) / tc::K2_NB <= tc::K2_MAX_BLOCKS, "(K+1)d = %d too large for the tcgen05 target kernel", nrows);
   if (B == 0) return SOCM_OK;
+  if (f16_default() != 0) return hx::launch_target_h(L, R, B, K, d, ldr, target, ldt, workspace, stream);
   const tc::K2Plan plan = tc::make_plan(nrows, kdim, d);
   unsigned char* tape = static_cast<unsigned char*>(workspace);
   tape += (1024 - (reinterpret_cast<uintptr_t>(tape) & 1023)) & 1023;

@@ -17,6 +17,11 @@ _SEED_COUNTER = [0]
 ENGINE = None
 
 
+def sync_engine(lib):
+    """Hand ENGINE to the library for the calls that have no engine flag of their own (the target GEMMs)."""
+    _lib.check(lib.socm_set_default_engine({None: -1, "tf32": 0, "f16": 1}[ENGINE]))
+
+
 def step_table(t: torch.Tensor, lmbd: float) -> torch.Tensor:
     """[5][K] fp32: dt_k, sqrt(lmbd dt_k), dt_k/lmbd, sqrt(dt_k/lmbd), t_k -- the per-step scalars of
     utils.py:38,47,95-98 computed with the same fp32 torch ops (dt from the fp32 linspace)."""
@@ -87,6 +92,7 @@ def rollout(sde, x0: torch.Tensor, t: torch.Tensor, lmbd: float, *, noises: Opti
     default hdims -> tcgen05 tensor-core kernel (3xTF32); ``force_ffma`` -> fp32 FFMA tile kernel;
     ``force_generic`` / other hdims -> shape-generic warp-per-path kernel."""
     lib = _lib.load()
+    sync_engine(lib)
     _lib.require_cuda(x0, "x0")
     desc = desc or describe_setting(sde, x0.device)
     B, K = int(x0.shape[0]), int(t.shape[0]) - 1

@@ -12,6 +12,7 @@ working set stays bounded for B up to 2^20 and beyond; every kernel accumulates.
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -118,7 +119,6 @@ class SOC_Solver(nn.Module):
             return 3
         n_tiles = (K + 1) * ((nb + 127) // 128)
         import ctypes
-        import os
         sms = ctypes.c_int(0)
         _lib.check(_lib.load().socm_device_info(ctypes.byref(sms), None))
         n_sm = max(int(sms.value), 1)
@@ -152,6 +152,7 @@ class SOC_Solver(nn.Module):
         if compute_L2_error and optimal_control is None:
             raise ValueError("compute_L2_error=True needs optimal_control (a callable (ts, states, t_is_tensor=True))")
         lib = _lib.load()
+        simulate.sync_engine(lib)
         sde = self.neural_sde
         dev = self.x0.device
         _lib.require_cuda(self.x0, "x0")
@@ -311,13 +312,15 @@ class SOC_Solver(nn.Module):
                 if simt_target:                                # fp32 SIMT GEMM
                     self._timed("target_bwd", 1, lib.socm_target_gemm_bwd_f32, _lib.ptr(G), _lib.ptr(R), nb, K, d, ldr,
                                 ldt, _lib.ptr(dL), 1, stream)
-                else:                                          # tcgen05, 3xTF32 (2 transposes + GEMM)
+                else:                                          # tcgen05: fp16 planes on kind::f16, or 3xTF32
                     if k2b_ws is None or k2b_nb != nb:
                         k2b_ws = torch.empty(int(lib.socm_target_gemm_bwd_tc_workspace_bytes(nb, K, d)), device=dev,
                                              dtype=torch.uint8)
                         k2b_nb = nb
-                    self._timed("target_bwd", 3, lib.socm_target_gemm_bwd_tc_f32, _lib.ptr(G), _lib.ptr(R), nb, K, d,
-                                ldr, ldt, _lib.ptr(dL), 1, k2b_ws.data_ptr(), stream)
+                    k2b_f16 = simulate.ENGINE != "tf32" and (simulate.ENGINE == "f16" or os.environ.get("SOCM_F16") != "0")
+                    self._timed("target_bwd", 4 if k2b_f16 else 3,   # absmax + 2 packs + GEMM | 2 transposes + GEMM
+                                lib.socm_target_gemm_bwd_tc_f32, _lib.ptr(G), _lib.ptr(R), nb, K, d, ldr, ldt, _lib.ptr(dL),
+                                1 | (_lib.TARGET_BWD_F16 if k2b_f16 else _lib.TARGET_BWD_TF32), k2b_ws.data_ptr(), stream)
             if stopping:
                 self._timed("target_bwd", 1, lib.socm_target_grouped_bwd_f32, _lib.ptr(G), _lib.ptr(R), q_idx.data_ptr(),
                             perm.data_ptr(), K + 1, nb, K, d, ldr, ldt, ldt, _lib.ptr(dLT), stream)
@@ -363,6 +366,7 @@ class SOC_Solver(nn.Module):
         The value F and a_m come from one extra UNet forward (socm_unet_forward_f32) and reductions over the
         rollout outputs (torch ops on the GPU); the UNet gradient from the same fused K3 kernels as SOCM."""
         lib = _lib.load()
+        simulate.sync_engine(lib)
         sde, dev = self.neural_sde, self.x0.device
         _lib.require_cuda(self.x0, "x0")
         desc = describe_setting(sde, dev)

@@ -24,6 +24,8 @@ def engine(request):
     simulate.ENGINE = request.param
     yield request.param
     simulate.ENGINE = None
+    from soc_matching_b200 import _lib
+    simulate.sync_engine(_lib.load())   # the library-side default follows (calls without an engine flag)
 
 
 NAMES = ["down_0", "down_1", "down_2", "res_0", "res_1", "res_2", "up_2", "up_1", "up_0"]
@@ -176,11 +178,13 @@ def test_tc_k3_is_the_default_for_large_batches_and_agrees_with_ffma():
 
 
 @pytest.mark.parametrize("d,K,B", [(10, 200, 300), (1, 150, 64), (20, 50, 129), (3, 7, 5)])
-def test_target_gemm_tc_matches_fp64(d, K, B):
-    """K2 forward on tcgen05 (csrc/target_tc.cu): target = R L^T with the block-triangular L, against
-    torch fp64 (3xTF32 with segmented accumulation: 6e-6 relative; the fp32 SIMT kernel: 2e-6)."""
-    from soc_matching_b200 import _lib
+def test_target_gemm_tc_matches_fp64(d, K, B, engine):
+    """K2 forward on tcgen05 (csrc/target_h.cu: fp16 hi/lo split on kind::f16; csrc/target_tc.cu: 3xTF32): target = R L^T
+    with the block-triangular L, against torch fp64 (segmented accumulation: 6e-6 relative; the fp32 SIMT kernel: 2e-6).
+    The operands span orders of magnitude (per-path scales on R, per-column scales on L)."""
+    from soc_matching_b200 import _lib, simulate
     lib = _lib.load()
+    simulate.sync_engine(lib)   # the `engine` fixture set simulate.ENGINE: this entry point has no engine flag
     g = torch.Generator(DEV).manual_seed(K)
     nrows, kdim = (K + 1) * d, (2 * K + 1) * d
     ldr, ldt = (kdim + 3) // 4 * 4, (nrows + 3) // 4 * 4
@@ -188,7 +192,8 @@ def test_target_gemm_tc_matches_fp64(d, K, B):
     i_of_row = torch.arange(nrows, device=DEV) // d
     col = torch.arange(ldr, device=DEV)
     L[(col[None, :] < 2 * i_of_row[:, None] * d) | (col[None, :] >= kdim)] = 0.0     # structure of mtable.build_L
-    R = torch.randn(B, ldr, device=DEV, generator=g)
+    L *= torch.exp(torch.randn(1, ldr, device=DEV, generator=g)) * 1e-2
+    R = torch.randn(B, ldr, device=DEV, generator=g) * torch.exp(2.0 * torch.randn(B, 1, device=DEV, generator=g)) * 50.0
     R[:, kdim:] = 0.0
     T = torch.full((B, ldt), float("nan"), device=DEV)
     ws = torch.empty(int(lib.socm_target_gemm_tc_workspace_bytes(K, d)), device=DEV, dtype=torch.uint8)
@@ -203,23 +208,26 @@ def test_target_gemm_tc_matches_fp64(d, K, B):
 
 
 @pytest.mark.parametrize("d,K,B", [(10, 200, 300), (1, 150, 64), (20, 50, 129), (3, 7, 5), (10, 100, 2048)])
-def test_target_gemm_bwd_tc_matches_fp64(d, K, B):
-    """K2 backward on tcgen05 (csrc/target_bwd_tc.cu): dL += G^T R on the block-upper-triangular part,
-    against torch fp64 (3xTF32, segmented accumulation: 1e-5 relative) and the fp32 SIMT kernel."""
+def test_target_gemm_bwd_tc_matches_fp64(d, K, B, engine):
+    """K2 backward on tcgen05 (csrc/target_bwd_h.cu: fp16 hi/lo planes on kind::f16; csrc/target_bwd_tc.cu: 3xTF32):
+    dL += G^T R on the block-upper-triangular part, against torch fp64 (segmented accumulation: 1e-5 relative) and the
+    fp32 SIMT kernel.  The operands span several orders of magnitude (per-path weights on G, per-column scales on R):
+    the fp16 engine scales by the exact maxima."""
     from soc_matching_b200 import _lib
     lib = _lib.load()
     g = torch.Generator(DEV).manual_seed(K + B)
     nrows, kdim = (K + 1) * d, (2 * K + 1) * d
     ldr, ldt = (kdim + 3) // 4 * 4, (nrows + 3) // 4 * 4
-    G = torch.randn(B, ldt, device=DEV, generator=g)
-    R = torch.randn(B, ldr, device=DEV, generator=g)
+    G = torch.randn(B, ldt, device=DEV, generator=g) * torch.exp(2.0 * torch.randn(B, 1, device=DEV, generator=g)) * 1e-3
+    R = torch.randn(B, ldr, device=DEV, generator=g) * torch.exp(torch.randn(1, ldr, device=DEV, generator=g)) * 30.0
     base = torch.randn(nrows, ldr, device=DEV, generator=g)
     i_of_row = torch.arange(nrows, device=DEV) // d
     col = torch.arange(ldr, device=DEV)
     keep = (col[None, :] >= 2 * i_of_row[:, None] * d) & (col[None, :] < kdim)
     dL = base.clone()
     ws = torch.empty(int(lib.socm_target_gemm_bwd_tc_workspace_bytes(B, K, d)), device=DEV, dtype=torch.uint8)
-    _lib.check(lib.socm_target_gemm_bwd_tc_f32(G.data_ptr(), R.data_ptr(), B, K, d, ldr, ldt, dL.data_ptr(), 1,
+    eng = _lib.TARGET_BWD_F16 if engine == "f16" else _lib.TARGET_BWD_TF32
+    _lib.check(lib.socm_target_gemm_bwd_tc_f32(G.data_ptr(), R.data_ptr(), B, K, d, ldr, ldt, dL.data_ptr(), 1 | eng,
                                                ws.data_ptr(), _lib.stream_ptr()))
     dL2 = base.clone()
     _lib.check(lib.socm_target_gemm_bwd_f32(G.data_ptr(), R.data_ptr(), B, K, d, ldr, ldt, dL2.data_ptr(), 1,
@@ -230,6 +238,12 @@ def test_target_gemm_bwd_tc_matches_fp64(d, K, B):
     assert torch.equal((dL - base)[~keep], torch.zeros_like(base)[~keep])          # structural zeros untouched
     assert rel_l2((dL - base).cpu(), want.cpu()) <= 1e-5
     assert rel_l2((dL2 - base).cpu(), want.cpu()) <= 1e-5
+    # without the accumulate bit the result replaces dL
+    dL3 = base.clone()
+    _lib.check(lib.socm_target_gemm_bwd_tc_f32(G.data_ptr(), R.data_ptr(), B, K, d, ldr, ldt, dL3.data_ptr(), eng,
+                                               ws.data_ptr(), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert rel_l2(dL3.cpu(), want.cpu()) <= 1e-5
 
 
 @pytest.mark.parametrize("kind,d,K,B,dense,stopping", [("ou_linear", 10, 40, 257, True, False),
