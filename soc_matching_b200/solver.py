@@ -291,9 +291,10 @@ class SOC_Solver(nn.Module):
                 if simt_target:                                # fp32 SIMT GEMM
                     self._timed("target", 1, lib.socm_target_gemm_f32, _lib.ptr(L.detach()), _lib.ptr(R), nb, K, d,
                                 ldr, _lib.ptr(target), ldt, stream)
-                else:                                          # tcgen05, 3xTF32 (tape pack + GEMM)
-                    self._timed("target", 2, lib.socm_target_gemm_tc_f32, _lib.ptr(L.detach()), _lib.ptr(R), nb, K, d,
-                                ldr, _lib.ptr(target), ldt, k2_ws.data_ptr(), stream)
+                else:   # tcgen05: fp16 split (2 x absmax + tape pack + GEMM) or 3xTF32 (tape pack + GEMM), simulate.sync_engine
+                    k2_f16 = simulate.ENGINE != "tf32" and (simulate.ENGINE == "f16" or os.environ.get("SOCM_F16") != "0")
+                    self._timed("target", 4 if k2_f16 else 2, lib.socm_target_gemm_tc_f32, _lib.ptr(L.detach()), _lib.ptr(R),
+                                nb, K, d, ldr, _lib.ptr(target), ldt, k2_ws.data_ptr(), stream)
             else:
                 # stopping index of every path (Phi(x) = -x_0 > 0, method.py:524-530) and the order that groups them
                 q_idx = ((wsp.states[..., 0] < 0).sum(dim=0) - 1).to(torch.int32).contiguous()
