@@ -16,6 +16,8 @@ gam = {"gamma": torch.tensor([2.0]), "gamma2": torch.tensor([1.0]), "gamma3": to
 from soc_matching_b200 import simulate
 for kind, d, K, B, stopping, flags in [("double_well", 10, 40, 130, False, ("tc", "f16")), ("double_well", 10, 40, 130, False, ("tc", "tf32")),
                                        ("double_well", 10, 40, 130, False, ("ffma",)),
+                                       # B >= 1024: the target GEMMs run on the tensor cores too (target_h.cu / target_tc.cu)
+                                       ("double_well", 10, 12, 1100, False, ("tc", "f16")), ("double_well", 10, 12, 1100, False, ("tc", "tf32")),
                                        ("ou_quadratic", 20, 4, 70, False, ("tc",)), ("molecular_dynamics", 1, 12, 140, True, ("tc",))]:
     simulate.ENGINE = "f16" if "f16" in flags else ("tf32" if "tf32" in flags else None)
     st = random_setting(kind, d, seed=1)
