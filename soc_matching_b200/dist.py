@@ -70,20 +70,35 @@ def sharded_loss_backward(solver, global_batch: int, algorithm: str = "SOCM", gr
     global value is the shard-size weighted mean.  With ``use_stopping_time`` (SOCM only, method.py:711-715)
     the reference divides by the sum of ALL stop indicators: each shard is normalised by its own sum z_r, so
     the ranks first all-reduce z (one fp64 scalar) and weight their shard by z_r / z before back-propagating --
-    the result does not depend on the world size."""
-    if algorithm in ("log-variance", "variance", "moment"):
-        raise NotImplementedError(
-            f"{algorithm!r} is a functional of the whole batch (a variance / second moment over all paths), not a mean "
-            "of per-path terms: its shards cannot be combined by summing gradients; run it on one rank")
+    the result does not depend on the world size.
+
+    ``log-variance`` and ``variance`` are functionals of the whole batch (a variance over all paths, method.py:800-856):
+    the solver sums the two moments over the ranks (``solver.batch_reduce``) and every rank differentiates the same global
+    value with respect to its own paths, so the gradients add up (no shard weighting) and the value is not summed."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world > global_batch:
         raise ValueError(f"world size {world} exceeds the global batch {global_batch}: a rank would own no path")
     lo, hi = shard_bounds(global_batch, rank, world)
     solver.path_offset = lo
-    out = solver.loss(hi - lo, algorithm=algorithm, **loss_kw)
+    whole_batch = algorithm in ("log-variance", "variance")
+
+    def _sum_over_ranks(t):
+        if world > 1:
+            dist.all_reduce(t, group=group)
+        return t
+
+    if whole_batch:
+        solver.batch_reduce, solver.global_batch = _sum_over_ranks, global_batch
+    try:
+        out = solver.loss(hi - lo, algorithm=algorithm, **loss_kw)
+    finally:
+        if whole_batch:
+            solver.batch_reduce, solver.global_batch = None, None
     stats = solver.last_stats.clone()
     share = (hi - lo) / float(global_batch)
+    if whole_batch:
+        share = 1.0
     if loss_kw.get("use_stopping_time") and algorithm == "SOCM":
         z_all = stats[2:3].clone()
         if world > 1:
@@ -95,7 +110,7 @@ def sharded_loss_backward(solver, global_batch: int, algorithm: str = "SOCM", gr
     # gradient this rank did not produce -- all ranks then send flat buffers of the same length.
     params = list(solver.parameters())
     grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
-    value = (out[0].detach() * share).reshape(1)
+    value = (out[0].detach() * (1.0 / world if whole_batch else share)).reshape(1)
     if world > 1:
         allreduce_flat(grads + [value], group)
         dist.all_reduce(stats, group=group)  # fp64 sums stay fp64

@@ -65,6 +65,8 @@ class SOC_Solver(nn.Module):
         self.y0 = nn.Parameter(torch.randn(1, device=x0.device))       # method.py:172 (unused by SOCM)
         self.sigma = neural_sde.sigma if sigma is None else sigma
         self.chunk_paths = None             # paths per kernel launch; None -> 4 full waves of 128-path tiles
+        self.batch_reduce = None            # data-parallel shards: sums a small fp64 tensor over the ranks (dist.py)
+        self.global_batch = None            # ... and the number of paths of all ranks together
         self.force_generic = False          # tests: run the shape-generic kernels
         self.force_ffma = False             # tests: fp32 FFMA tile kernels instead of the tcgen05 kernels
         self.force_tc = False               # tests: tcgen05 K3 even for small batches
@@ -427,7 +429,18 @@ class SOC_Solver(nn.Module):
             obj = torch.mean((S_leaf + self.y0) ** 2 * w2)
         else:
             sums = S_leaf if algorithm == "log-variance" else torch.exp(S_leaf)
-            obj = B / (B - 1) * (torch.mean(sums**2 * w2) - torch.mean(sums * w2) ** 2)
+            if self.batch_reduce is None:
+                obj = B / (B - 1) * (torch.mean(sums**2 * w2) - torch.mean(sums * w2) ** 2)
+            else:
+                # data-parallel shard (dist.sharded_loss_backward): the functional is a variance over ALL paths, so the
+                # first and second moments are summed over the ranks; autograd sees this shard's terms, the other
+                # ranks' enter as constants, and the ranks' gradients of the same global value add up to its gradient
+                Bg = int(self.global_batch)
+                m1, m2 = torch.sum(sums * w2), torch.sum(sums**2 * w2)
+                tot = self.batch_reduce(torch.stack([m1.detach(), m2.detach()]).double())
+                m1g = m1 + (tot[0] - m1.detach().double()).to(m1.dtype)
+                m2g = m2 + (tot[1] - m2.detach().double()).to(m2.dtype)
+                obj = Bg / (Bg - 1) * (m2g / Bg - (m1g / Bg) ** 2)
         a_m, = torch.autograd.grad(obj, S_leaf, retain_graph=algorithm == "moment")
         # ---- gradient: K3 with path weights a_m, point weights delta / (2 lmbd), target -sigma^{-T}(c + sqrt(lmbd/delta) eps)
         ldt = ((K + 1) * d + 3) // 4 * 4

@@ -27,7 +27,7 @@ gam = {"gamma": torch.tensor([6.0]), "gamma2": torch.tensor([1.0]), "gamma3": to
 torch.manual_seed(123)                      # same Philox key on every rank
 sde = make_product_sde(st, seeded_unet(d, [256, 128, 64], 3), seeded_mnet(d, [128, 128], 4), gam, [256, 128, 64], [128, 128], dev)
 solver = sb.SOC_Solver(sde, torch.zeros(d, device=dev), None, T=1.0, num_steps=K, lmbd=1.0, d=d, sigma=sde.sigma)
-val, mw, sw = sdist.sharded_loss_backward(solver, B, "SOCM")
+val, mw, sw = sdist.sharded_loss_backward(solver, B, os.environ.get("SOCM_ALGO", "SOCM"))
 if rank == 0:
     torch.save({"val": val.cpu(), "mw": mw.cpu(), "sw": sw.cpu(),
                 "grads": {n: p.grad.cpu() for n, p in sde.named_parameters() if p.grad is not None}}, os.environ["SOCM_OUT"])
@@ -36,9 +36,9 @@ if world > 1:
 '''
 
 
-def _run(world, out):
+def _run(world, out, algo="SOCM"):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    env = dict(os.environ, SOCM_ROOT=ROOT, SOCM_OUT=out)
+    env = dict(os.environ, SOCM_ROOT=ROOT, SOCM_OUT=out, SOCM_ALGO=algo)
     if world == 1:
         cmd = [sys.executable, "-c", WORKER]
     else:
@@ -49,10 +49,12 @@ def _run(world, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_ranks_equal_one(tmp_path):
+@pytest.mark.parametrize("algo", ["SOCM", "log-variance", "moment"])
+def test_two_gpu_ranks_equal_one(tmp_path, algo):
+    """log-variance is a functional of the whole batch: the ranks exchange its two moments (dist.sharded_loss_backward)."""
     from helpers import rel_l2
-    one = _run(1, str(tmp_path / "one.pt"))
-    two = _run(2, str(tmp_path / "two.pt"))
+    one = _run(1, str(tmp_path / "one.pt"), algo)
+    two = _run(2, str(tmp_path / "two.pt"), algo)
     assert abs(float(two["val"]) - float(one["val"])) <= 1e-5 * abs(float(one["val"]))
     assert abs(float(two["mw"]) - float(one["mw"])) <= 1e-6 * abs(float(one["mw"]))
     for n, g in one["grads"].items():
