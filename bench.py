@@ -297,7 +297,7 @@ def gpu_arm(args):
     # ---- rooflines (rank 0's shard).  achieved = ALGORITHMIC fp32 FLOP of all launches of the timed region / the sum
     # of their CUDA-event times; peak = measured dense bf16 GEMM (sustained: the kernels run inside a long step).
     # Every product of the UNet kernels is three tensor-core MMAs (fp32-class accuracy): fp16 hi/lo splits on kind::f16
-    # (the engine this workload runs, csrc/unet_h.cuh) or 3xTF32 (csrc/unet_tc.cuh; K2 always), so the ceiling of the
+    # (the engine this workload runs, csrc/unet_h.cuh, target_h.cu) or 3xTF32 (csrc/unet_tc.cuh), so the ceiling of the
     # executed arithmetic is the measured dense rate of that kind / 3; both fractions are reported.
     n_local = hi - lo
     points = (K + 1) * n_local * args.steps
