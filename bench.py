@@ -169,12 +169,15 @@ def zero_grads(solver):
 
 
 def kernel_source_hash():
-    """sha256 over the K3 kernel sources: a committed ncu traffic figure is only reported while it still describes
-    the kernels that are being timed."""
+    """sha256 over the CODE of the K3 kernel sources (// comments and blank lines stripped): a committed ncu traffic figure
+    is only reported while it still describes the kernels that are being timed."""
     h = hashlib.sha256()
     for f in ("loss_h.cu", "wgrad_h.cu", "unet_h.cuh", "loss_tc.cuh", "wgrad_tables.cuh", "umma.cuh"):
-        with open(os.path.join(ROOT, "soc_matching_b200", "csrc", f), "rb") as fh:
-            h.update(fh.read())
+        with open(os.path.join(ROOT, "soc_matching_b200", "csrc", f), "r") as fh:
+            for line in fh:
+                code = line.split("//", 1)[0].strip()
+                if code:
+                    h.update(code.encode() + b"\n")
     return h.hexdigest()[:16]
 
 

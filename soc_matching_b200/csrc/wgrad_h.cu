@@ -322,7 +322,7 @@ int launch_wgrad_h(const unsigned char* scratch, int n_tiles, int d, const float
 }  // namespace hx
 }  // namespace socm
 
-// debug / test entry: run the fp16 K3b on a caller-built scratch (tests/test_gpu_wgrad_tc.py)
+// debug / test entry: run the fp16 K3b on a caller-built scratch (tests/test_gpu_wgrad_h.py)
 extern "C" int socm_debug_wgrad_h(const void* scratch, int32_t n_tiles, int32_t d, const float* scales, float* grad,
                                   float* aux, void* stream) {
   return socm::hx::launch_wgrad_h(static_cast<const unsigned char*>(scratch), n_tiles, d, scales, grad, aux,

@@ -1,7 +1,8 @@
-// wgrad_tables.cuh -- work description shared by the two weight-gradient kernels (wgrad_tc.cu: fp32 scratch, 3xTF32;
-// wgrad_h.cu: fp16 hi|lo scratch, kind::f16).  Both scratches have the same geometry (loss_tc.cuh): a feature row is
-// 128 bytes for the 32 points of a tile quarter, a feature block 32 rows = 4 KB, so the stage / product / output
-// tables below serve both.
+// wgrad_tables.cuh -- work description of the weight-gradient kernels: the record types and the stage / product /
+// output tables of wgrad_tc.cu (fp32 scratch, 3xTF32).  wgrad_h.cu (fp16 hi|lo scratch, kind::f16) uses the same
+// record types and region offsets with its own tables (one stage fewer).  Both scratches have the same block geometry
+// (loss_tc.cuh): tile -> 4 quarters of 32 points -> 59 feature blocks of 32 features = 4 KB; they differ inside a block
+// (fp32 K-major rows with the 128-byte swizzle here, fp16 planes in MN-major core matrices there).
 #pragma once
 #include "loss_tc.cuh"
 
