@@ -19,7 +19,7 @@ namespace hx {
 
 using namespace umma;
 
-constexpr int T_NT = 320;       // warps 0-3 producers, 4-7 epilogue, 8 MMA, 9 tape
+constexpr int T_NT = 448;       // warps 0-7 producers (two threads per path, 16 columns each), 8-11 epilogue, 12 MMA, 13 tape
 constexpr int T_NB = 256;       // rows of L per block (= accumulator columns)
 constexpr int T_MAX_BLOCKS = 64;
 constexpr int T_SEG = 32;       // chunks per accumulation segment (6 MMAs each)
@@ -118,14 +118,14 @@ __global__ void __launch_bounds__(T_NT, 1)
       mbar_init(&bars[W_EMPTY + s], 1);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&bars[CH_FULL + b], 4);
+      mbar_init(&bars[CH_FULL + b], 8);
       mbar_init(&bars[CH_EMPTY + b], 1);
       mbar_init(&bars[ACC_FULL + b], 1);
       mbar_init(&bars[ACC_EMPTY + b], 4);
     }
     mbar_init_fence();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  if (warp == 12) tmem_alloc(tmem_slot, 512);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -133,24 +133,24 @@ __global__ void __launch_bounds__(T_NT, 1)
   const uint32_t ring_s = smem_addr(smem + SM_RING), chunk_s = smem_addr(smem + SM_CHUNK);
   const float s_r = pow2_scale(__uint_as_float(mx[0]), T_TARGET), s_l = pow2_scale(__uint_as_float(mx[1]), T_TARGET);
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ===================================================== producers: R row pieces -> A chunks (fp16 hi / lo, scaled)
-    const int p = tid;
+    const int p = tid & (TP - 1), half = tid >> 7;   // this thread converts columns [16 half, 16 half + 16) of every chunk
     uint32_t cu = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int m = t * TP + p;
-      const float* row = R + (size_t)(m < B ? m : 0) * ldr;
-      auto load = [&](int c, float4* x) {   // 32 columns of this thread's row: one 128-byte line
+      const float* row = R + (size_t)(m < B ? m : 0) * ldr + 16 * half;
+      auto load = [&](int c, float4* x) {   // 16 columns of this thread's row: half a 128-byte line
 #pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4) {
-          const int col = 32 * c + 4 * q4;
-          x[q4] = (m < B && col < ldr) ? __ldg(reinterpret_cast<const float4*>(row + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int col = 32 * c + 16 * half + 4 * q4;
+          x[q4] = (m < B && col < ldr) ? __ldg(reinterpret_cast<const float4*>(row + 32 * c + 4 * q4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }  // ldr % 4 == 0; padding is zero
       };
       // the loads of the next chunk are in flight while the current one is converted (the row pieces come from L2 / DRAM:
       // without this the producers, not the MMAs, set the pace)
       int nt = 0, c = plan.chunk_begin[0];
-      float4 cur[8];
+      float4 cur[4];
       load(c, cur);
       while (nt < plan.n_blocks) {
         int nt2 = nt, c2 = c + 1;
@@ -158,9 +158,9 @@ __global__ void __launch_bounds__(T_NT, 1)
           ++nt2;
           c2 = nt2 < plan.n_blocks ? plan.chunk_begin[nt2] : 0;
         }
-        float4 nx[8];
+        float4 nx[4];
         if (nt2 < plan.n_blocks) load(c2, nx);
-        {   // ... and the line of the chunk T_AHEAD further down the sequence is pulled towards the SM (DRAM latency ~ 2 chunks)
+        if (half == 0) {   // ... and the line of the chunk T_AHEAD further down the sequence is pulled towards the SM
           int ntp = nt, cp = c + T_AHEAD;
           if (cp >= plan.n_chunks && ntp + 1 < plan.n_blocks) {
             cp = plan.chunk_begin[ntp + 1] + (cp - plan.n_chunks);
@@ -169,31 +169,28 @@ __global__ void __launch_bounds__(T_NT, 1)
           if (m < B && cp < plan.n_chunks && 32 * cp < ldr)
             asm volatile("prefetch.global.L1 [%0];" ::"l"(row + 32 * cp));
         }
-        float v[32];
+        float v[16];
 #pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4) {
+        for (int q4 = 0; q4 < 4; ++q4) {
           v[4 * q4] = cur[q4].x * s_r; v[4 * q4 + 1] = cur[q4].y * s_r; v[4 * q4 + 2] = cur[q4].z * s_r; v[4 * q4 + 3] = cur[q4].w * s_r;
         }
-        uint32_t hi[16], lo[16];
+        uint32_t hi[8], lo[8];
         split16(v, hi, lo);
-        split16(v + 16, hi + 8, lo + 8);
         const int b = cu & 1;
         mbar_wait_parked(&bars[CH_EMPTY + b], ((cu >> 1) & 1) ^ 1);
-        unsigned char* chunk = smem + SM_CHUNK + b * CHUNK_BYTES;
-        store_chunk16(chunk, p, 0, hi, lo);
-        store_chunk16(chunk, p, 2, hi + 8, lo + 8);
+        store_chunk16(smem + SM_CHUNK + b * CHUNK_BYTES, p, 2 * half, hi, lo);
         fence_async_smem();
         warp_arrive(&bars[CH_FULL + b]);
         ++cu;
 #pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4) cur[q4] = nx[q4];
+        for (int q4 = 0; q4 < 4; ++q4) cur[q4] = nx[q4];
         nt = nt2;
         c = c2;
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < 12) {
     // ===================================================== epilogue: accumulator -> target rows
-    const int p = tid - 128;
+    const int p = tid - 256;
     const uint32_t lane_t = tm + ((uint32_t)((warp & 3) * 32) << 16);
     const float inv = 1.f / (s_r * s_l);
     uint32_t ia = 0;
@@ -236,7 +233,7 @@ __global__ void __launch_bounds__(T_NT, 1)
         }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == 12) {
     // ===================================================== MMA issue
     uint32_t ws = 0, cm = 0, ia = 0;
     for (int g = 0; g < my_tiles; ++g) {
@@ -282,7 +279,7 @@ __global__ void __launch_bounds__(T_NT, 1)
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tm, 512);
+  if (warp == 12) tmem_dealloc(tm, 512);
 }
 
 // workspace: [tape][2 x uint32 maxima]; never larger than the 3xTF32 tape (same bytes per L entry)
