@@ -211,11 +211,19 @@ __device__ __forceinline__ uint32_t pack_h2(float lo_elem, float hi_elem) {
 __device__ __forceinline__ float2 h2_to_f2(uint32_t h) {
   return __half22float2(*reinterpret_cast<const __half2*>(&h));
 }
-// (a, b) -> hi = f16x2(a, b), lo = f16x2(a - hi.a, b - hi.b)
+// (a, b) -> hi = f16x2(a, b), lo = f16x2(a - hi.a, b - hi.b).  The residual a - hi.a is one mixed-precision FMA
+// (fma.rn.f32.f16 = SASS FHFMA, which reads either half of the packed register: hi.a * (-1) + a, exact) instead of an
+// unpack (HADD2.F32) and an FADD: the split of a pair is 4 instructions, and the split is what the epilogue warps of the
+// fp16 engine spend their issue slots on.
 __device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
   hi = pack_h2(a, b);
-  const float2 f = h2_to_f2(hi);
-  lo = pack_h2(a - f.x, b - f.y);
+  unsigned short h0, h1;
+  asm("mov.b32 {%0, %1}, %2;" : "=h"(h0), "=h"(h1) : "r"(hi));
+  const unsigned short neg1 = 0xBC00;   // -1.0 in fp16
+  float ra, rb;
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(ra) : "h"(h0), "h"(neg1), "f"(a));
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(rb) : "h"(h1), "h"(neg1), "f"(b));
+  lo = pack_h2(ra, rb);
 }
 
 // true in exactly one lane of a fully converged warp (the same lane every time)
