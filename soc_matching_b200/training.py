@@ -57,7 +57,12 @@ class TrainingStatistics:
 
 
 class Trainer:
-    """One object per (solver, algorithm): ``step(itr)`` is the loop body of main.py:279-393."""
+    """One object per (solver, algorithm): ``step(itr)`` is the loop body of main.py:279-393.
+
+    ``normalization_const`` is the starting value of the running normalisation constant that main.py:316-323 divides the
+    loss by; the reference initialises it with the Monte-Carlo estimate of main.py:118-121
+    (``soc_matching_b200.normalization_constant``).  With the default 1.0 the bias-corrected EMA (utils.py:389-396) jumps
+    to mean(w) after the first iteration and the reported loss rescales accordingly."""
 
     # main.py:316-322: which objectives are divided by the normalisation constant (variance: by its square)
     _NORMALISED = ("SOCM_const_M", "SOCM_exp", "SOCM", "SOCM_adjoint", "cross_entropy")
